@@ -1,0 +1,183 @@
+"""Generate the committed golden fixtures from the REAL reference (run in the build container only).
+
+    PYTHONPATH=/root/repo python tests/golden/make_golden.py
+
+Imports the reference modules where they lie under /root/reference through `oracle/ref_shim.py`, loads the
+seeded synthetic weights of `taste_spokenlm_b200.synth` into the reference's own `TasteAudioTower`
+(`load_state_dict(strict=True)`), runs the reference's own `WhisperFrontend.forward` (WF:87-113) and
+`TasteAudioTower.forward` (MT:108-211) on seeded synthetic inputs, and stores small outputs / sub-sampled
+intermediates as .npz.  Inputs and weights are NOT stored: they are regenerated from the seeds recorded here.
+"""
+import os
+import sys
+import json
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_shim                      # noqa: E402
+from taste_spokenlm_b200 import synth            # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+torch.set_grad_enabled(False)
+
+CASES = {
+    # name: (config name, weight seed, batch seed, durations [s], token counts)
+    "tower_tiny": ("TINY", 1234, 0, [10.0, 3.7, 30.0], [30, 11, 64]),
+    "tower_tiny_single_word": ("TINY", 1234, 5, [2.0, 5.0], [1, 7]),
+    "tower_small": ("SMALL", 4321, 1, [12.5, 30.0], [40, 80]),
+    "tower_full": ("FULL", 1234, 0, [10.0, 30.0], [30, 64]),
+}
+
+
+def ref_frontend(fe, wav, n_samples):
+    feats = []
+    for b in range(wav.shape[0]):
+        n = int(n_samples[b])
+        f, _ = fe(wav[b:b + 1, :n], torch.tensor([n]))
+        feats.append(f)
+    return torch.cat(feats)
+
+
+def tower_case(name, cfg_name, wseed, bseed, durs, toks, fe):
+    cfg = getattr(synth, cfg_name)
+    tower = ref_shim.build_reference_tower(d_model=cfg.d_model, enc_layers=cfg.enc_layers, dec_layers=cfg.dec_layers,
+                                           heads=cfg.heads, ffn=cfg.ffn, vocab=cfg.vocab)
+    W = synth.random_weights(cfg, wseed)
+    tower.load_state_dict(W, strict=True)
+    batch = synth.synth_batch(bseed, durs, toks)
+    feats = ref_frontend(fe, batch["wav"], batch["n_samples"])
+    B = feats.shape[0]
+    fl = torch.tensor([3000] * B)
+    out = tower(batch["asr_token_ids"], batch["asr_token_lengths"], feats, fl, asr_word_ids=batch["asr_word_ids"])
+    agg = tower(batch["asr_token_ids"], batch["asr_token_lengths"], feats, fl, asr_word_ids=batch["asr_word_ids"],
+                skip_vq_in_audio_encoder=True)
+    enc = tower.audio_joint_encoder_segmenter.audio_encoder(feats, fl, output_hidden_states=6)["encoded_feats"]
+    cs = 8 if cfg.d_model > 256 else 1
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"),
+        meta=json.dumps(dict(config=cfg_name, weight_seed=wseed, batch_seed=bseed, durations=durs, tokens=toks,
+                             chan_stride=cs)),
+        feats_sub=feats[:, ::50, :].numpy(),
+        feats_sum=feats.double().sum(dim=(1, 2)).numpy(),
+        h_last_sub=enc["last_hidden"][:, ::100, ::cs].numpy(),
+        h_target_sub=enc["6"][:, ::100, ::cs].numpy(),
+        aggregated=agg["audio_unit_embeds"].numpy(),
+        audio_unit_embeds=out["audio_unit_embeds"].numpy(),
+        audio_unit_lengths=out["audio_unit_lengths"].numpy(),
+        quantized_indices=out["quantized_indices"].numpy(),
+    )
+    print(name, "ok", tuple(out["quantized_indices"].shape))
+
+
+def frontend_cases(fe):
+    specs = [("1s", 16000), ("10s", 160000), ("29.99s", 479840), ("30s", 480000), ("33s_trimmed", 528000),
+             ("odd", 123457)]
+    d = {}
+    names = []
+    for i, (nm, n) in enumerate(specs):
+        wav = synth.synth_waveform(100 + i, n)[None]
+        f, l = fe(wav, torch.tensor([n]))
+        d[f"{nm}_sub"] = f[0, ::25, :].numpy()
+        d[f"{nm}_sum"] = f.double().sum().numpy()
+        d[f"{nm}_len"] = l.numpy()
+        names.append([nm, 100 + i, n])
+    # silence (hits the 1e-10 clamp everywhere) and a loud square-ish wave
+    z = torch.zeros(1, 8000)
+    f, _ = fe(z, torch.tensor([8000]))
+    d["silence_sub"] = f[0, ::25, :].numpy()
+    np.savez_compressed(os.path.join(OUT, "frontend.npz"), meta=json.dumps(names), **d)
+    print("frontend ok")
+
+
+def rvq_case():
+    cfg = synth.FULL
+    AQ = sys.modules["taste_speech.modules_taste.audio_quantizer"]
+    vq = AQ.RVQAudioQuantizer(codebook_dim=256, codebook_size=512, decay=0.99, dim=1280, kmeans_init=True,
+                              kmeans_iters=100, num_quantizers=4, quantize_dropout=True).eval()
+    W = synth.random_weights(cfg, 77)
+    sd = {k[len("vq."):]: v for k, v in W.items() if k.startswith("vq.")}
+    vq.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(9)
+    z = torch.randn(3, 50, 1280, generator=g)
+    z = z + 0.7 * torch.randn(1, 1, 1280, generator=g)
+    lens = torch.tensor([50, 17, 1])
+    mask = torch.arange(50)[None] < lens[:, None]
+    r = vq(z, mask=mask)
+    rvq = vq.rvq
+    idx = r["quantized_indices"]
+    np.savez_compressed(
+        os.path.join(OUT, "rvq.npz"),
+        meta=json.dumps(dict(weight_seed=77, z_seed=9, lens=[50, 17, 1])),
+        quantized_feats=r["quantized_feats"].numpy(), quantized_indices=idx.numpy(),
+        output_from_indices=rvq.get_output_from_indices(idx).numpy(),
+        code_from_indices=rvq.get_code_from_indices(idx).numpy(),
+        indices_from_code=rvq.get_indices_from_code(rvq.project_in(z), mask=mask).numpy(),
+    )
+    print("rvq ok")
+
+
+def pooling_cases():
+    JES = sys.modules["taste_speech.modules_taste.audio_joint_encoder_segmenter"]
+    f = JES.WhisperAudioJointEncoderSegmenter._convert_word_ids_to_words_index
+    cases = [
+        ([[0, 0, 0, 0]], [2]), ([[0, 0]], [2]), ([[0, 0, 1, 1, 1, 2, 0, 0]], [7]), ([[0, 1, 2, 3]], [5]),
+        ([[0, 0, 1, 1], [0, 1, 1, 0]], [5, 4]), ([[0, 1, 1, 2, 2, 2, 3, 3, 0, 0, 0]], [9]),
+        ([[0, 0, 0, 1, 1]], [4]), ([[3, 3, 3]], [4]),
+    ]
+    res = []
+    for wid, ln in cases:
+        out = f(None, torch.tensor(wid, dtype=torch.int32), torch.tensor(ln))
+        res.append(dict(word_ids=wid, lengths=ln, words_index=[list(map(int, t)) for t in out]))
+    json.dump(res, open(os.path.join(OUT, "word_pooling.json"), "w"), indent=0)
+    print("pooling ok")
+
+
+def mapping_case():
+    import importlib
+    MT = sys.modules["taste_speech.modeling_taste"]
+    cls = MT.TasteForCausalLM
+    g = torch.Generator().manual_seed(3)
+    B, T, L, Q = 3, 12, 16, 4
+    asr_len = torch.tensor([12, 7, 1]); llm_len = torch.tensor([16, 9, 2])
+    asr_wid = torch.zeros(B, T, dtype=torch.int32); llm_wid = torch.zeros(B, L, dtype=torch.int32)
+    for b in range(B):
+        nw = 0
+        for t in range(int(asr_len[b])):
+            if t > 0 and torch.rand(1, generator=g).item() < 0.55:
+                nw += 1
+            asr_wid[b, t] = nw
+        # llm tokenisation of the same words with different sub-word splits
+        per = [1 + int(torch.randint(0, 3, (1,), generator=g)) for _ in range(nw + 1)]
+        seq = [w for w, c in enumerate(per) for _ in range(c)][: int(llm_len[b])]
+        llm_len[b] = len(seq)
+        llm_wid[b, : len(seq)] = torch.tensor(seq, dtype=torch.int32)
+    llm_wid = llm_wid[:, : int(llm_len.max())].contiguous()          # collate pads to the longest row
+    idx = torch.randint(0, 512, (B, T, Q), generator=g)
+    idx = torch.where((torch.arange(T)[None] < asr_len[:, None])[..., None], idx, torch.full_like(idx, -1))
+    sm = cls._get_word_start_mapping_matrix(None, asr_wid, llm_wid, asr_len, llm_len)
+    # generate_mask_from_length truncates to max length: pad back to [B, L, T]
+    llm = torch.bmm(sm, idx[:, : sm.shape[2]].float()) - (sm.sum(dim=-1, keepdim=True) == 0).float()
+    llm = llm.to(idx.dtype)
+    np.savez_compressed(os.path.join(OUT, "llm_mapping.npz"), asr_indices=idx.numpy(), asr_len=asr_len.numpy(),
+                        llm_len=llm_len.numpy(), asr_wid=asr_wid.numpy(), llm_wid=llm_wid.numpy(),
+                        llm_indices=llm.numpy())
+    print("mapping ok", tuple(llm.shape))
+
+
+if __name__ == "__main__":
+    fe = ref_shim.build_reference_frontend()
+    which = sys.argv[1:] or list(CASES) + ["frontend", "rvq", "pooling", "mapping"]
+    for name in which:
+        if name in CASES:
+            tower_case(name, *CASES[name], fe)
+    if "frontend" in which:
+        frontend_cases(fe)
+    ref_shim.build_reference_tower(d_model=128, enc_layers=1, heads=2, ffn=128, vocab=51866)   # ensures modules imported
+    if "rvq" in which:
+        rvq_case()
+    if "pooling" in which:
+        pooling_cases()
+    if "mapping" in which:
+        mapping_case()
