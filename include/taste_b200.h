@@ -1,0 +1,199 @@
+/* taste_b200.h — C ABI of the B200-native TASTE speech-tokenization path (libtaste_b200.so).
+ *
+ * The reference (dienruei123/TASTE-SpokenLM) has NO native/FFI layer on this path: everything below replaces
+ * PyTorch module calls.  Each entry point cites the reference interface it stands in for, using the
+ * abbreviations of SURVEY.md:
+ *   WF  taste_speech/modules_taste/cosyvoice/whisper_frontend.py
+ *   JES taste_speech/modules_taste/audio_joint_encoder_segmenter.py
+ *   CW  taste_speech/modules_taste/cosyvoice/customized_whisper.py
+ *   MT  taste_speech/modeling_taste.py
+ *   AQ  taste_speech/modules_taste/audio_quantizer.py
+ *   RVQ taste_speech/modules_taste/vq/residual_vq.py     VQ  .../vq/vector_quantize_pytorch.py
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers unless a name ends in `_host`;
+ *   - the library never allocates or frees device memory: the caller passes a workspace sized by
+ *     taste_ws_bytes(); every launch is enqueued on the caller's stream (`stream` is a cudaStream_t passed as
+ *     void*); no host synchronisation inside;
+ *   - return value: 0 = success; negative = argument error (TASTE_E_*); positive = cudaError_t / CUresult;
+ *     taste_last_error() returns a thread-local message for the last non-zero return;
+ *   - there is no CPU fallback: on a machine without an sm_100 GPU every compute entry point fails.
+ */
+#ifndef TASTE_B200_H_
+#define TASTE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TASTE_ABI_VERSION 1
+
+#define TASTE_E_ARG        (-1)  /* null pointer / bad size */
+#define TASTE_E_SHAPE      (-2)  /* geometry not supported by the kernels (see taste_handle_create) */
+#define TASTE_E_WORKSPACE  (-3)  /* workspace too small */
+#define TASTE_E_NO_DEVICE  (-4)  /* no sm_100 device / driver entry point missing */
+
+#define TASTE_N_FFT      400
+#define TASTE_HOP        160
+#define TASTE_N_SAMPLES  480000   /* WF:30 pad_samples */
+#define TASTE_N_FRAMES   3000     /* JES:97 expected_seq_length */
+#define TASTE_N_MELS     128
+#define TASTE_ENC_FRAMES 1500
+#define TASTE_DFT_LD     224      /* padded leading dim of the DFT tables */
+
+typedef struct taste_handle_s* taste_handle_t;
+
+/* Geometry (distil-large-v3 + CFG:146-155 by default). */
+typedef struct {
+  int32_t d_model;          /* 1280; multiple of 128 */
+  int32_t heads;            /* 20; head_dim must be 64 */
+  int32_t ffn;              /* 5120; multiple of 128 */
+  int32_t enc_layers;       /* 32 */
+  int32_t dec_layers;       /* 2 */
+  int32_t vocab;            /* 51866 */
+  int32_t max_target_pos;   /* 448 */
+  int32_t codebook_dim;     /* 256 (fixed by the RVQ kernel) */
+  int32_t codebook_size;    /* 512 (fixed by the RVQ kernel) */
+  int32_t num_quantizers;   /* 4; <= 8 */
+  int32_t target_layer;     /* 6: hidden state ENTERING this encoder layer is the value source (JES:192-193) */
+  int32_t reserved;
+} taste_dims_t;
+
+/* One Whisper encoder layer (CW:649-716).  Matrices are bf16 row-major [out, in]; vectors fp32. */
+typedef struct {
+  const float* ln1_w;  const float* ln1_b;     /* self_attn_layer_norm */
+  const void*  wqkv;   const float* bqkv;      /* [3D, D]: q rows pre-scaled by head_dim^-0.5 (CW:342), k bias = 0 (CW:315) */
+  const void*  wo;     const float* bo;        /* out_proj */
+  const float* ln2_w;  const float* ln2_b;     /* final_layer_norm */
+  const void*  w1;     const float* b1;        /* fc1 [FF, D] */
+  const void*  w2;     const float* b2;        /* fc2 [D, FF] */
+} taste_enc_layer_t;
+
+/* One aggregator (Whisper decoder) layer (CW:719-833). */
+typedef struct {
+  const float* ln1_w;  const float* ln1_b;     /* self_attn_layer_norm */
+  const void*  wqkv;   const float* bqkv;      /* causal self-attention, packed as above */
+  const void*  wo;     const float* bo;
+  const float* lnx_w;  const float* lnx_b;     /* encoder_attn_layer_norm */
+  const void*  wq_x;   const float* bq_x;      /* encoder_attn.q_proj (pre-scaled) */
+  const void*  wk_x;                           /* encoder_attn.k_proj, no bias; applied to the LAST encoder state */
+  const void*  wv_x;   const float* bv_x;      /* encoder_attn.v_proj; applied to the layer-`target_layer` input */
+  const void*  wo_x;   const float* bo_x;
+  const float* ln2_w;  const float* ln2_b;     /* final_layer_norm */
+  const void*  w1;     const float* b1;
+  const void*  w2;     const float* b2;
+} taste_dec_layer_t;
+
+typedef struct {
+  taste_dims_t dims;
+  /* log-mel tables (WF:56-85; A1): folded DFT twiddles and the sparse Slaney filterbank */
+  const float*   dft_cos;       /* [200][TASTE_DFT_LD]: cos(2*pi*k*n/400), n = row+1 (1..199; row 199 unused), k = col */
+  const float*   dft_sin;       /* [200][TASTE_DFT_LD]: sin(2*pi*k*n/400) */
+  const float*   hann;          /* [400] periodic Hann */
+  const int32_t* mel_start;     /* [128] first non-zero bin of each mel filter */
+  const int32_t* mel_count;     /* [128] number of non-zero bins */
+  const float*   mel_weight;    /* [128][TASTE_MEL_MAXW] non-zero weights, zero padded */
+  /* encoder stem (JES:174-181) */
+  const void*  conv1_w;  const float* conv1_b;   /* bf16 [D, 3*128], k = tap*128 + c */
+  const void*  conv2_w;  const float* conv2_b;   /* bf16 [D, 3*D],   k = tap*D + c */
+  const float* enc_pos;                          /* fp32 [1500, D] embed_positions.weight */
+  const taste_enc_layer_t* enc;                  /* HOST array [enc_layers] */
+  const float* enc_ln_w;  const float* enc_ln_b; /* encoder.layer_norm */
+  /* aggregator (CW:1160-1437) */
+  const float* tok_emb;                          /* fp32 [vocab, D] */
+  const float* dec_pos;                          /* fp32 [max_target_pos, D] */
+  const taste_dec_layer_t* dec;                  /* HOST array [dec_layers] */
+  const float* dec_ln_w;  const float* dec_ln_b;
+  /* RVQ (RVQ:102-170, VQ:266-340); all fp32 */
+  const float* rvq_win_t;     /* [D][256]      project_in.weight transposed */
+  const float* rvq_bin;       /* [256] */
+  const float* rvq_code_t;    /* [Q][256][512] codebooks transposed (distance pass) */
+  const float* rvq_code;      /* [Q][512][256] codebooks (gather) */
+  const float* rvq_code_sq;   /* [Q][512]      |e|^2 */
+  const float* rvq_wout_t;    /* [256][D]      project_out.weight transposed */
+  const float* rvq_bout;      /* [D] */
+} taste_weights_t;
+
+#define TASTE_MEL_MAXW 16
+
+/* --- library ---------------------------------------------------------------------------------------------- */
+int         taste_abi_version(void);
+const char* taste_last_error(void);
+
+/* Build an immutable handle from a weights descriptor (the struct and its host arrays are copied; the device
+ * buffers they point to stay owned by the caller and must outlive the handle).
+ * Stands in for TasteAudioTower.__init__ + checkpoint load (MT:34-95, JES:281-328). */
+int taste_handle_create(const taste_weights_t* w, taste_handle_t* out);
+int taste_handle_destroy(taste_handle_t h);
+
+/* Workspace bytes needed by the calls below for a batch of `batch` utterances whose assembled transcripts
+ * (prefix + tokens + 1) total `sum_tokens` rows. */
+size_t taste_ws_bytes(taste_handle_t h, int batch, int sum_tokens);
+
+/* --- R1: WhisperFrontend.forward (WF:87-113) -------------------------------------------------------------- */
+/* wav: fp32 [batch, wav_stride]; n_samples: int32 [batch] (samples valid in each row; <= 480000 are used, the
+ * rest of the 30 s window is zero, WF:98-99).  feats_f32: [batch,3000,128] (nullable); feats_bf16 (nullable):
+ * same layout in bf16 for the encoder stem.  At least one output must be given. */
+int taste_logmel_f32(taste_handle_t h, const float* wav, const int32_t* n_samples, int batch, int64_t wav_stride,
+                     float* feats_f32, void* feats_bf16, void* ws, size_t ws_bytes, void* stream);
+
+/* --- R2/R3: WhisperAudioEncoderForJoint.forward (JES:133-223) --------------------------------------------- */
+/* feats_f32 [batch,3000,128] (or feats_bf16 if feats_f32 is NULL) -> h_last, h_target: bf16 [batch,1500,D]
+ * (final-LayerNorm state and the hidden state entering layer `target_layer`). */
+int taste_encoder_fwd(taste_handle_t h, const float* feats_f32, const void* feats_bf16, int batch, void* h_last_bf16,
+                      void* h_target_bf16, void* ws, size_t ws_bytes, void* stream);
+
+/* --- R4/R5: token assembly (MT:144-152) + WhisperDecoder.forward with dict K/V (JES:377-388, CW:1200-1437) - */
+/* tokens: int32 packed [sum_tokens] assembled ids; cu_tokens: int32 [batch+1] row offsets.
+ * dec_out: fp32 packed [sum_tokens, D] = decoder final LayerNorm state at every assembled position. */
+int taste_aggregator_fwd(taste_handle_t h, const void* h_last_bf16, const void* h_target_bf16, const int32_t* tokens,
+                         const int32_t* cu_tokens, int batch, int sum_tokens, int max_tokens, float* dec_out, void* ws,
+                         size_t ws_bytes, void* stream);
+
+/* --- R6: prefix skip + word pooling + EOS drop (JES:393-458, MT:170-172) ----------------------------------- */
+/* dec_out packed as above (row 4+t of utterance b is transcript position t); word_ids int32 [batch,tmax] (padded
+ * with the caller's pad value, normally 0 — runs are formed on the padded row exactly as JES:437-458);
+ * token_lengths int32 [batch].  z: fp32 [batch,tmax,D]; rows t >= token_lengths[b] are written as 0. */
+int taste_word_pool_f32(const float* dec_out, const int32_t* cu_tokens, const int32_t* word_ids,
+                        const int32_t* token_lengths, int batch, int tmax, int d_model, float* z, void* stream);
+
+/* --- R7: RVQAudioQuantizer.forward -> ResidualVQ.forward (AQ:109-124, RVQ:359-490) ------------------------- */
+/* z fp32 [batch,tmax,in_dim]; lengths int32 [batch] (mask = t < lengths[b], modules_taste/utils.py:5-8; NULL =
+ * all valid).  in_dim == d_model: project_in is applied (RVQ:371); in_dim == 256: `z` is already a code
+ * (ResidualVQ.get_indices_from_code, RVQ:258-357).  indices int64 [batch,tmax,Q] (-1 at masked rows);
+ * quantized fp32 [batch,tmax,D] (nullable) = project_out(sum of codes) (RVQ:470). */
+int taste_rvq_encode_f32(taste_handle_t h, const float* z, const int32_t* lengths, int batch, int tmax, int in_dim,
+                         int64_t* indices, float* quantized, void* stream);
+/* ResidualVQ.get_output_from_indices / get_code_from_indices (RVQ:183-242): indices int64 [n,Q] (-1 -> zero code).
+ * out fp32 [n, D] if project_out != 0 else [n, 256]. */
+int taste_rvq_decode_f32(taste_handle_t h, const int64_t* indices, int n, int project_out, float* out, void* stream);
+
+/* --- (f)1: TasteForCausalLM.extract_vq epilogue (MT:1438-1450, MT:1877-1881) ------------------------------- */
+/* asr_indices int64 [batch,tmax,Q] -> llm_indices int64 [batch,lmax,Q] (-1 where no word-start match). */
+int taste_map_to_llm_tokens(const int64_t* asr_indices, const int32_t* asr_word_ids, const int32_t* asr_lengths,
+                            const int32_t* llm_word_ids, const int32_t* llm_lengths, int batch, int tmax, int lmax,
+                            int num_q, int64_t* llm_indices, void* stream);
+
+/* --- building blocks exported for kernel-level parity tests and micro-benchmarks ---------------------------- */
+/* C[M,N] = epilogue(A[M,K] @ W[N,K]^T + bias).  A, W bf16 row-major; bias fp32 [N] (nullable).
+ * epilogue: 0 = bf16 out; 1 = GELU(erf) then bf16 out; 2 = fp32 out += (residual add in place, CW:692, 702);
+ * 3 = fp32 out.  Requires N % 128 == 0, K % 64 == 0. */
+int taste_gemm_bf16(const void* a, const void* w, const float* bias, void* out, int m, int n, int k, int epilogue,
+                    void* stream);
+/* y = LayerNorm(x) (eps 1e-5, CW:660): x fp32 [rows, d]; y bf16 (out_bf16 != 0) or fp32. */
+int taste_layernorm_f32(const float* x, const float* w, const float* b, void* y, int rows, int d, int out_bf16,
+                        void* stream);
+/* softmax(Q K^T [+ causal mask]) V per head (CW:377-394); q is expected pre-scaled.  bf16, head_dim 64.
+ * Row b of q/o starts at cu_q[b] (or b*q_len if cu_q is NULL) and has cu_q[b+1]-cu_q[b] (or q_len) rows; same
+ * for k/v with cu_kv / kv_len.  ld* are row strides in elements. */
+int taste_attention_bf16(const void* q, const void* k, const void* v, void* o, int ldq, int ldk, int ldv, int ldo,
+                         const int32_t* cu_q, const int32_t* cu_kv, int q_len, int kv_len, int batch, int heads,
+                         int causal, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TASTE_B200_H_ */

@@ -1,0 +1,108 @@
+"""ctypes binding of libtaste_b200.so (include/taste_b200.h).  There is no fallback: if the library is missing or a
+declared symbol is absent, load() raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtaste_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "taste_b200.h")
+
+DFT_LD = 224
+MEL_MAXW = 16
+N_FRAMES = 3000
+N_MELS = 128
+ENC_FRAMES = 1500
+N_SAMPLES = 480000
+
+EPI_BF16, EPI_GELU_BF16, EPI_RESID_F32, EPI_F32 = 0, 1, 2, 3
+
+p = C.c_void_p
+
+
+class Dims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "d_model", "heads", "ffn", "enc_layers", "dec_layers", "vocab", "max_target_pos", "codebook_dim",
+        "codebook_size", "num_quantizers", "target_layer", "reserved")]
+
+
+class EncLayer(C.Structure):
+    _fields_ = [(n, p) for n in ("ln1_w", "ln1_b", "wqkv", "bqkv", "wo", "bo", "ln2_w", "ln2_b", "w1", "b1", "w2", "b2")]
+
+
+class DecLayer(C.Structure):
+    _fields_ = [(n, p) for n in (
+        "ln1_w", "ln1_b", "wqkv", "bqkv", "wo", "bo", "lnx_w", "lnx_b", "wq_x", "bq_x", "wk_x", "wv_x", "bv_x",
+        "wo_x", "bo_x", "ln2_w", "ln2_b", "w1", "b1", "w2", "b2")]
+
+
+class Weights(C.Structure):
+    _fields_ = [("dims", Dims)] + [(n, p) for n in (
+        "dft_cos", "dft_sin", "hann", "mel_start", "mel_count", "mel_weight",
+        "conv1_w", "conv1_b", "conv2_w", "conv2_b", "enc_pos", "enc", "enc_ln_w", "enc_ln_b",
+        "tok_emb", "dec_pos", "dec", "dec_ln_w", "dec_ln_b",
+        "rvq_win_t", "rvq_bin", "rvq_code_t", "rvq_code", "rvq_code_sq", "rvq_wout_t", "rvq_bout")]
+
+
+_SIGS = {
+    "taste_abi_version": (C.c_int, []),
+    "taste_last_error": (C.c_char_p, []),
+    "taste_handle_create": (C.c_int, [C.POINTER(Weights), C.POINTER(p)]),
+    "taste_handle_destroy": (C.c_int, [p]),
+    "taste_ws_bytes": (C.c_size_t, [p, C.c_int, C.c_int]),
+    "taste_logmel_f32": (C.c_int, [p, p, p, C.c_int, C.c_int64, p, p, p, C.c_size_t, p]),
+    "taste_encoder_fwd": (C.c_int, [p, p, p, C.c_int, p, p, p, C.c_size_t, p]),
+    "taste_aggregator_fwd": (C.c_int, [p, p, p, p, p, C.c_int, C.c_int, C.c_int, p, p, C.c_size_t, p]),
+    "taste_word_pool_f32": (C.c_int, [p, p, p, p, C.c_int, C.c_int, C.c_int, p, p]),
+    "taste_rvq_encode_f32": (C.c_int, [p, p, p, C.c_int, C.c_int, C.c_int, p, p, p]),
+    "taste_rvq_decode_f32": (C.c_int, [p, p, C.c_int, C.c_int, p, p]),
+    "taste_map_to_llm_tokens": (C.c_int, [p, p, p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, p, p]),
+    "taste_gemm_bf16": (C.c_int, [p, p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, p]),
+    "taste_layernorm_f32": (C.c_int, [p, p, p, p, C.c_int, C.c_int, C.c_int, p]),
+    "taste_attention_bf16": (C.c_int, [p, p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, p, p, C.c_int, C.c_int,
+                                       C.c_int, C.c_int, C.c_int, p]),
+}
+
+_lib = None
+
+
+class TasteError(RuntimeError):
+    pass
+
+
+def declared_symbols(header_path: str = HEADER_PATH):
+    """Every function the public header declares (used by the symbol-coverage test)."""
+    txt = open(header_path).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(taste_[a-z0-9_]+)\s*\(", txt)))
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TasteError(f"{LIB_PATH} not found: run `python __graft_entry__.py` (build()) first; there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGS.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise TasteError(f"libtaste_b200.so does not export {name}") from e
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().taste_last_error().decode(errors="replace")
+        raise TasteError(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr(t):
+    """Device/host pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())

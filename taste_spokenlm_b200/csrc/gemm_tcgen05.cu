@@ -1,0 +1,383 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a: TMA -> smem ring -> tcgen05.mma (fp32 accumulators in TMEM,
+// double buffered) -> tcgen05.ld epilogue with fused bias / GELU(erf) / residual / positional add.
+//
+// Serves every linear layer of the Whisper encoder and the aggregator (CW:342,365-366,407,699-701) and,
+// through the multi-tap A addressing, the two stem convolutions as implicit GEMMs (JES:174-175): tap t of the k=3
+// kernel is a GEMM over the same activations shifted by one row, and the zero padding is TMA out-of-bounds fill.
+//
+// Roles (256 threads, 1 CTA / SM):  warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4-7 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31 = rows of the 128-row tile).
+#include <stdio.h>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace taste {
+
+constexpr int BM = 128;
+constexpr int BK = 64;            // 64 bf16 = 128 B = one swizzle row
+constexpr int kGemmThreads = 256;
+
+struct GemmParams {
+  int rows_out;            // valid output rows per batch entry
+  int m_tiles_per_batch;
+  int n_tiles;
+  int total_tiles;
+  int kb_per_tap;
+  int taps;
+  int tap_s[3];
+  int tap_dr[3];
+  const float* bias;
+  void* out;
+  int ldc;
+  const float* pos;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr uint32_t kABytes = BM * BK * 2;
+  static constexpr uint32_t kBBytes = BN * BK * 2;
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr uint32_t kTmemCols = 2 * BN;       // two accumulator stages
+  static constexpr size_t kSmemBytes = 1024 /*align slack*/ + size_t(kStages) * kStageBytes + 256 /*barriers*/;
+};
+
+template <int EPI>
+TASTE_DEVINL void epilogue_chunk(const uint32_t (&acc)[32], const GemmParams& p, int64_t grow, int row_in_batch, int n0) {
+  float v[32];
+  if (p.bias != nullptr) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = __ldg(b4 + j);
+      v[4 * j + 0] = __uint_as_float(acc[4 * j + 0]) + b.x;
+      v[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + b.y;
+      v[4 * j + 2] = __uint_as_float(acc[4 * j + 2]) + b.z;
+      v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + b.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+  }
+  if (EPI == EPI_GELU_BF16 || EPI == EPI_GELU_POS_F32) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf<true>(v[j]);
+  }
+  if (EPI == EPI_BF16 || EPI == EPI_GELU_BF16) {
+    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + grow * p.ldc + n0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 u;
+      u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+      u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+      u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+      u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+      o[j] = u;
+    }
+  } else {
+    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + grow * p.ldc + n0);
+    if (EPI == EPI_RESID_F32) {
+      float4 r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = o[j];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        r[j].x += v[4 * j + 0];
+        r[j].y += v[4 * j + 1];
+        r[j].z += v[4 * j + 2];
+        r[j].w += v[4 * j + 3];
+        o[j] = r[j];
+      }
+    } else if (EPI == EPI_GELU_POS_F32) {
+      const float4* pp = reinterpret_cast<const float4*>(p.pos + int64_t(row_in_batch) * p.ldc + n0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 q = __ldg(pp + j);
+        o[j] = make_float4(v[4 * j + 0] + q.x, v[4 * j + 1] + q.y, v[4 * j + 2] + q.z, v[4 * j + 3] + q.w);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+  }
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                         const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + size_t(kStages) * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;   // [2] accumulator ready   (MMA -> epilogue)
+  uint64_t* tempty_bar = tfull_bar + 2;        // [2] accumulator drained (epilogue -> MMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);          // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int kb_total = p.taps * p.kb_per_tap;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        const int mg = tile / p.n_tiles;
+        const int b = mg / p.m_tiles_per_batch;
+        const int mt = mg - b * p.m_tiles_per_batch;
+        for (int kb = 0; kb < kb_total; ++kb) {
+          const int tap = kb / p.kb_per_tap;
+          const int kc = kb - tap * p.kb_per_tap;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + size_t(stage) * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          const int ts = tap == 0 ? p.tap_s[0] : (tap == 1 ? p.tap_s[1] : p.tap_s[2]);
+          const int tr = tap == 0 ? p.tap_dr[0] : (tap == 1 ? p.tap_dr[1] : p.tap_dr[2]);
+          tma_load_4d(sa, &tma_a, &full_bar[stage], kc * BK, ts, mt * BM + tr, b);
+          tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, nt * BN);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = umma_idesc(BM, BN, /*bf16*/ 1, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(as * BN);
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + size_t(stage) * Cfg::kStageBytes);
+          const uint64_t da = umma_desc_k_sw128(sa);
+          const uint64_t db = umma_desc_k_sw128(sa + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128-B swizzle row: +2 in the (addr >> 4) field
+            umma_ss(d_tmem, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);      // frees the smem slot when these MMAs retire
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[as]);           // accumulator complete
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles;
+      const int mg = tile / p.n_tiles;
+      const int b = mg / p.m_tiles_per_batch;
+      const int mt = mg - b * p.m_tiles_per_batch;
+      const int row_in_batch = mt * BM + q * 32 + lane;
+      const bool valid = row_in_batch < p.rows_out;
+      const int64_t grow = int64_t(b) * p.rows_out + row_in_batch;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(taddr + uint32_t(c * 32), acc);
+        tmem_ld_wait();
+        if (valid) epilogue_chunk<EPI>(acc, p, grow, row_in_batch, nt * BN + c * 32);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int EPI>
+static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  auto kern = gemm_bf16_tcgen05_kernel<BN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    TASTE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmCfg<BN>::kSmemBytes));
+    configured = true;
+  }
+  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  kern<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, stream>>>(ta, tb, p);
+  TASTE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <int BN>
+static int launch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int epi, cudaStream_t s) {
+  switch (epi) {
+    case EPI_BF16: return launch_cfg<BN, EPI_BF16>(ta, tb, p, s);
+    case EPI_GELU_BF16: return launch_cfg<BN, EPI_GELU_BF16>(ta, tb, p, s);
+    case EPI_RESID_F32: return launch_cfg<BN, EPI_RESID_F32>(ta, tb, p, s);
+    case EPI_F32: return launch_cfg<BN, EPI_F32>(ta, tb, p, s);
+    case EPI_GELU_POS_F32: return launch_cfg<BN, EPI_GELU_POS_F32>(ta, tb, p, s);
+  }
+  return set_error(TASTE_E_ARG, "gemm: unknown epilogue %d", epi);
+}
+
+int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
+  if (!d.a || !d.w || !d.out) return set_error(TASTE_E_ARG, "gemm: null pointer");
+  if (d.k_inner % BK != 0 || d.n % 128 != 0 || d.taps < 1 || d.taps > 3)
+    return set_error(TASTE_E_SHAPE, "gemm: need K %% 64 == 0 and N %% 128 == 0 (k_inner=%d n=%d taps=%d)", d.k_inner,
+                     d.n, d.taps);
+  if (d.rows_out <= 0 || d.batches <= 0) return 0;
+  if (d.epilogue == EPI_GELU_POS_F32 && !d.pos) return set_error(TASTE_E_ARG, "gemm: pos table missing");
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return set_error(TASTE_E_NO_DEVICE, "cuTensorMapEncodeTiled entry point unavailable");
+
+  const int m_tiles = (d.rows_out + BM - 1) / BM;
+  const int64_t tiles256 = (d.n % 256 == 0) ? int64_t(m_tiles) * d.batches * (d.n / 256) : 0;
+  const int bn = (tiles256 >= num_sms()) ? 256 : 128;
+
+  CUtensorMap ta, tb;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d.k_inner, (cuuint64_t)d.s_count, (cuuint64_t)d.rows_in, (cuuint64_t)d.batches};
+    cuuint64_t strides[3] = {(cuuint64_t)d.s_stride, (cuuint64_t)d.r_stride, (cuuint64_t)d.b_stride};
+    cuuint32_t box[4] = {BK, 1, BM, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d.a), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error((int)r, "gemm: tensor map A encode failed (%d)", (int)r);
+  }
+  {
+    const int64_t ktot = int64_t(d.taps) * d.k_inner;
+    cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)d.n};
+    cuuint64_t strides[1] = {(cuuint64_t)(ktot * 2)};
+    cuuint32_t box[2] = {BK, (cuuint32_t)bn};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d.w), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error((int)r, "gemm: tensor map B encode failed (%d)", (int)r);
+  }
+  GemmParams p;
+  p.rows_out = d.rows_out;
+  p.m_tiles_per_batch = m_tiles;
+  p.n_tiles = d.n / bn;
+  p.total_tiles = m_tiles * d.batches * p.n_tiles;
+  p.kb_per_tap = d.k_inner / BK;
+  p.taps = d.taps;
+  for (int i = 0; i < 3; ++i) {
+    p.tap_s[i] = d.tap_s[i];
+    p.tap_dr[i] = d.tap_dr[i];
+  }
+  p.bias = d.bias;
+  p.out = d.out;
+  p.ldc = d.ldc;
+  p.pos = d.pos;
+  return bn == 256 ? launch_epi<256>(ta, tb, p, d.epilogue, stream) : launch_epi<128>(ta, tb, p, d.epilogue, stream);
+}
+
+int gemm_plain(const void* a, const void* w, const float* bias, void* out, int m, int n, int k, int epilogue,
+               cudaStream_t stream) {
+  GemmDesc d;
+  d.a = a;
+  d.k_inner = k;
+  d.s_count = 1;
+  d.rows_in = m;
+  d.rows_out = m;
+  d.batches = 1;
+  d.s_stride = int64_t(k) * 2;
+  d.r_stride = int64_t(k) * 2;
+  d.b_stride = int64_t(m) * k * 2;
+  d.taps = 1;
+  d.w = w;
+  d.n = n;
+  d.bias = bias;
+  d.out = out;
+  d.ldc = n;
+  d.epilogue = epilogue;
+  return launch_gemm(d, stream);
+}
+
+}  // namespace taste

@@ -1,0 +1,89 @@
+// Host-side internal interfaces between the translation units of libtaste_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/taste_b200.h"
+
+namespace taste {
+
+// ---- error plumbing (api.cu) ----
+int set_error(int code, const char* fmt, ...);
+#define TASTE_CUDA_OK(expr)                                                                        \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) return ::taste::set_error((int)_e, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+// ---- GEMM (gemm_tcgen05.cu) ----
+enum GemmEpilogue {
+  EPI_BF16 = 0,          // out bf16 = acc + bias
+  EPI_GELU_BF16 = 1,     // out bf16 = gelu(acc + bias)
+  EPI_RESID_F32 = 2,     // out fp32 += acc + bias
+  EPI_F32 = 3,           // out fp32 = acc + bias
+  EPI_GELU_POS_F32 = 4,  // out fp32 = gelu(acc + bias) + pos[row_in_batch][col]
+};
+
+// out[b*R + r, :] = epi( sum_tap A[b, r + tap_dr[tap], tap_s[tap], :] @ W[:, tap*k_inner : (tap+1)*k_inner]^T + bias )
+// A is addressed as a 4-D tensor {k_inner, s_count, rows_in, batches} with byte strides; rows outside
+// [0, rows_in) read as zero (TMA out-of-bounds fill) which implements the convolution's zero padding.
+struct GemmDesc {
+  const void* a = nullptr;
+  int k_inner = 0;
+  int s_count = 1;
+  int rows_in = 0;            // addressable rows per batch entry in A
+  int rows_out = 0;           // output rows per batch entry (R)
+  int batches = 1;
+  int64_t s_stride = 0, r_stride = 0, b_stride = 0;   // bytes
+  int taps = 1;
+  int tap_s[3] = {0, 0, 0};
+  int tap_dr[3] = {0, 0, 0};
+  const void* w = nullptr;    // bf16 [n, taps*k_inner]
+  int n = 0;
+  const float* bias = nullptr;
+  void* out = nullptr;
+  int ldc = 0;
+  int epilogue = EPI_BF16;
+  const float* pos = nullptr;
+};
+int launch_gemm(const GemmDesc& d, cudaStream_t stream);
+int gemm_plain(const void* a, const void* w, const float* bias, void* out, int m, int n, int k, int epilogue,
+               cudaStream_t stream);
+
+// ---- attention (attention_mma.cu) ----
+struct AttnDesc {
+  const void *q, *k, *v;
+  void* o;
+  int ldq, ldk, ldv, ldo;
+  const int32_t* cu_q;
+  const int32_t* cu_kv;
+  int q_len, kv_len;     // fixed lengths when cu_* is null; otherwise upper bounds used for the grid
+  int batch, heads, causal;
+};
+int launch_attention(const AttnDesc& d, cudaStream_t stream);
+
+// ---- elementwise (elementwise.cu) ----
+int launch_layernorm(const float* x, const float* w, const float* b, void* y, int rows, int d, bool out_bf16,
+                     cudaStream_t stream);
+int launch_cast_bf16(const float* x, void* y, int64_t n, cudaStream_t stream);
+int launch_embed(const int32_t* tokens, const int32_t* cu_tokens, int batch, int sum_tokens, const float* tok_emb,
+                 const float* pos_emb, int d, int vocab, int max_pos, float* out, cudaStream_t stream);
+int launch_word_pool(const float* dec_out, const int32_t* cu_tokens, const int32_t* word_ids,
+                     const int32_t* token_lengths, int batch, int tmax, int d, float* z, cudaStream_t stream);
+int launch_map_llm(const int64_t* asr_indices, const int32_t* asr_wid, const int32_t* asr_len, const int32_t* llm_wid,
+                   const int32_t* llm_len, int batch, int tmax, int lmax, int nq, int64_t* out, cudaStream_t stream);
+
+// ---- log-mel (logmel.cu) ----
+int launch_logmel(const taste_weights_t& w, const float* wav, const int32_t* n_samples, int batch, int64_t wav_stride,
+                  float* feats_f32, void* feats_bf16, float* scratch_logspec, unsigned int* scratch_max,
+                  cudaStream_t stream);
+
+// ---- RVQ (rvq.cu) ----
+int launch_rvq_encode(const taste_weights_t& w, const float* z, const int32_t* lengths, int batch, int tmax, int in_dim,
+                      int64_t* indices, float* quantized, cudaStream_t stream);
+int launch_rvq_decode(const taste_weights_t& w, const int64_t* indices, int n, bool project_out, float* out,
+                      cudaStream_t stream);
+
+}  // namespace taste

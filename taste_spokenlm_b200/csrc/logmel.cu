@@ -1,0 +1,200 @@
+// Whisper log-mel front-end (WF:56-113), fused per 64-frame tile:
+//   pad/trim to 30 s + reflect padding (index arithmetic, no padded copy) -> periodic-Hann window ->
+//   400-point real DFT, folded over the n <-> 400-n symmetry so only 199 x 201 twiddle products are needed per
+//   frame -> |X|^2 -> sparse Slaney mel projection (394 non-zeros) -> log10(clamp 1e-10) -> per-utterance max.
+// A second small kernel applies the `max - 8` floor and the (x+4)/4 scaling and emits fp32 and/or bf16 features.
+// Arithmetic is fp32 FFMA throughout: the 80 dB dynamic range kept by the `max - 8` floor rules out a single
+// bf16 tensor-core pass (SURVEY §7 hard part 6).
+#include "common.cuh"
+#include "internal.h"
+
+namespace taste {
+
+constexpr int LM_FRAMES = 64;          // frames per CTA
+constexpr int LM_THREADS = 256;        // 8 frame groups x 32 bin lanes
+constexpr int LM_FPT = 8;              // frames per thread
+constexpr int LM_KPT = 7;              // bins per thread: k = lane + 32*j  (224 >= 201)
+constexpr int LM_NH = 199;             // folded terms n = 1..199
+constexpr int LM_LDF = 65;             // padded frame stride of the folded arrays (bank-conflict free both ways)
+constexpr int LM_LDP = 209;            // padded bin stride of the power tile
+constexpr int LM_SMEM = (2 * 200 * LM_LDF + LM_FRAMES) * 4;   // E, O, y200
+
+static_assert(LM_FRAMES * LM_LDP * 4 <= 2 * 200 * LM_LDF * 4, "power tile must fit in the folded arrays it aliases");
+
+__device__ __forceinline__ float padded_sample(const float* __restrict__ wav, int n_valid, int i) {
+  int j = i - TASTE_N_FFT / 2;                                   // torch.stft(center=True): reflect pad 200
+  if (j < 0) j = -j;
+  else if (j >= TASTE_N_SAMPLES) j = 2 * (TASTE_N_SAMPLES - 1) - j;
+  return j < n_valid ? __ldg(wav + j) : 0.f;                     // whisper.pad_or_trim zero padding (WF:98-99)
+}
+
+__device__ __forceinline__ unsigned int float_to_ordered(float f) {
+  const unsigned int b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(unsigned int k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
+__global__ void __launch_bounds__(LM_THREADS, 1)
+logmel_tile_kernel(const float* __restrict__ wav, const int32_t* __restrict__ n_samples, int64_t wav_stride,
+                   const float* __restrict__ dft_cos, const float* __restrict__ dft_sin, const float* __restrict__ hann,
+                   const int32_t* __restrict__ mel_start, const int32_t* __restrict__ mel_count,
+                   const float* __restrict__ mel_weight, float* __restrict__ logspec, unsigned int* __restrict__ umax) {
+  extern __shared__ float lm_smem[];
+  float* sE = lm_smem;                       // [200][65]  w[n] * (x[n] + x[400-n]),  row n-1
+  float* sO = sE + 200 * LM_LDF;             // [200][65]  w[n] * (x[n] - x[400-n])
+  float* sY200 = sO + 200 * LM_LDF;          // [64]
+  float* sP = lm_smem;                       // aliases sE/sO after the DFT: [64][209]
+  __shared__ float s_red[LM_THREADS / 32];
+
+  const int b = blockIdx.y;
+  const int f0 = blockIdx.x * LM_FRAMES;
+  const int tid = threadIdx.x;
+  const float* w = wav + int64_t(b) * wav_stride;
+  int n_valid = n_samples ? n_samples[b] : TASTE_N_SAMPLES;
+  n_valid = max(0, min(n_valid, TASTE_N_SAMPLES));
+
+  // ---- stage 1: folded, windowed frames ----
+  for (int idx = tid; idx < LM_FRAMES * 200; idx += LM_THREADS) {
+    const int f = idx / 200;
+    const int n = idx - f * 200 + 1;                  // 1..200
+    const int base = (f0 + f) * TASTE_HOP;
+    if (n <= LM_NH) {
+      const float a = padded_sample(w, n_valid, base + n);
+      const float c = padded_sample(w, n_valid, base + TASTE_N_FFT - n);
+      const float hw = __ldg(hann + n);
+      sE[(n - 1) * LM_LDF + f] = hw * a + hw * c;
+      sO[(n - 1) * LM_LDF + f] = hw * a - hw * c;
+    } else {
+      sY200[f] = __ldg(hann + 200) * padded_sample(w, n_valid, base + 200);
+      sE[199 * LM_LDF + f] = 0.f;
+      sO[199 * LM_LDF + f] = 0.f;
+    }
+  }
+  __syncthreads();
+
+  // ---- stage 2: DFT as a register-tiled fp32 product against the twiddle tables ----
+  const int fg = tid >> 5;                    // frame group: frames fg*8 .. fg*8+7
+  const int lane = tid & 31;
+  float re[LM_FPT][LM_KPT], im[LM_FPT][LM_KPT];
+#pragma unroll
+  for (int i = 0; i < LM_FPT; ++i)
+#pragma unroll
+    for (int j = 0; j < LM_KPT; ++j) re[i][j] = im[i][j] = 0.f;
+
+#pragma unroll 2
+  for (int n = 0; n < LM_NH; ++n) {
+    float c[LM_KPT], s[LM_KPT];
+#pragma unroll
+    for (int j = 0; j < LM_KPT; ++j) {
+      c[j] = __ldg(dft_cos + n * TASTE_DFT_LD + lane + 32 * j);
+      s[j] = __ldg(dft_sin + n * TASTE_DFT_LD + lane + 32 * j);
+    }
+#pragma unroll
+    for (int i = 0; i < LM_FPT; ++i) {
+      const float e = sE[n * LM_LDF + fg * LM_FPT + i];
+      const float o = sO[n * LM_LDF + fg * LM_FPT + i];
+#pragma unroll
+      for (int j = 0; j < LM_KPT; ++j) {
+        re[i][j] = fmaf(e, c[j], re[i][j]);
+        im[i][j] = fmaf(o, s[j], im[i][j]);
+      }
+    }
+  }
+  float y200[LM_FPT];
+#pragma unroll
+  for (int i = 0; i < LM_FPT; ++i) y200[i] = sY200[fg * LM_FPT + i];
+  __syncthreads();                            // everyone finished reading sE/sO: reuse as the power tile
+#pragma unroll
+  for (int j = 0; j < LM_KPT; ++j) {
+    const int k = lane + 32 * j;
+    if (k <= 200) {
+      const float sgn = (k & 1) ? -1.f : 1.f;          // y[0] = 0 (periodic Hann), y[200] * (-1)^k
+#pragma unroll
+      for (int i = 0; i < LM_FPT; ++i) {
+        const float r = re[i][j] + sgn * y200[i];
+        sP[(fg * LM_FPT + i) * LM_LDP + k] = r * r + im[i][j] * im[i][j];
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- stage 3: mel projection, log10, running max ----
+  float lmax = -INFINITY;
+  const int m = tid & 127;
+  const int ms = __ldg(mel_start + m);
+  const int mc = __ldg(mel_count + m);
+  float wgt[TASTE_MEL_MAXW];
+#pragma unroll
+  for (int j = 0; j < TASTE_MEL_MAXW; ++j) wgt[j] = __ldg(mel_weight + m * TASTE_MEL_MAXW + j);
+  for (int f = tid >> 7; f < LM_FRAMES; f += 2) {
+    if (f0 + f >= TASTE_N_FRAMES) break;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < TASTE_MEL_MAXW; ++j)
+      if (j < mc) acc = fmaf(wgt[j], sP[f * LM_LDP + ms + j], acc);
+    const float lg = log10f(fmaxf(acc, 1e-10f));
+    logspec[(int64_t(b) * TASTE_N_FRAMES + f0 + f) * TASTE_N_MELS + m] = lg;
+    lmax = fmaxf(lmax, lg);
+  }
+  lmax = warp_max(lmax);
+  if (lane == 0) s_red[tid >> 5] = lmax;
+  __syncthreads();
+  if (tid == 0) {
+    float v = s_red[0];
+    for (int i = 1; i < LM_THREADS / 32; ++i) v = fmaxf(v, s_red[i]);
+    if (v > -INFINITY) atomicMax(umax + b, float_to_ordered(v));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+logmel_finish_kernel(const float* __restrict__ logspec, const unsigned int* __restrict__ umax, float* __restrict__ out_f32,
+                     __nv_bfloat16* __restrict__ out_bf16) {
+  const int b = blockIdx.y;
+  const float floor_v = ordered_to_float(umax[b]) - 8.0f;                 // WF:79-82
+  const int64_t base = int64_t(b) * TASTE_N_FRAMES * TASTE_N_MELS;
+  const int n4 = TASTE_N_FRAMES * TASTE_N_MELS / 4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(logspec + base)[i];
+    v.x = (fmaxf(v.x, floor_v) + 4.0f) / 4.0f;                            // WF:83
+    v.y = (fmaxf(v.y, floor_v) + 4.0f) / 4.0f;
+    v.z = (fmaxf(v.z, floor_v) + 4.0f) / 4.0f;
+    v.w = (fmaxf(v.w, floor_v) + 4.0f) / 4.0f;
+    if (out_f32) reinterpret_cast<float4*>(out_f32 + base)[i] = v;
+    if (out_bf16) {
+      uint2 u;
+      u.x = pack_bf16x2(v.x, v.y);
+      u.y = pack_bf16x2(v.z, v.w);
+      reinterpret_cast<uint2*>(out_bf16 + base)[i] = u;
+    }
+  }
+}
+
+int launch_logmel(const taste_weights_t& w, const float* wav, const int32_t* n_samples, int batch, int64_t wav_stride,
+                  float* feats_f32, void* feats_bf16, float* scratch_logspec, unsigned int* scratch_max,
+                  cudaStream_t stream) {
+  if (!wav || (!feats_f32 && !feats_bf16)) return set_error(TASTE_E_ARG, "logmel: null pointer");
+  if (!w.dft_cos || !w.dft_sin || !w.hann || !w.mel_start || !w.mel_count || !w.mel_weight)
+    return set_error(TASTE_E_ARG, "logmel: tables missing from the handle");
+  if (batch <= 0) return 0;
+  static bool configured = false;
+  if (!configured) {
+    TASTE_CUDA_OK(cudaFuncSetAttribute(logmel_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_SMEM));
+    configured = true;
+  }
+  // un-normalised log spectrum goes to the fp32 output when present (normalised in place), else to scratch
+  float* logspec = feats_f32 ? feats_f32 : scratch_logspec;
+  TASTE_CUDA_OK(cudaMemsetAsync(scratch_max, 0, sizeof(unsigned int) * batch, stream));
+  dim3 grid((TASTE_N_FRAMES + LM_FRAMES - 1) / LM_FRAMES, batch);
+  logmel_tile_kernel<<<grid, LM_THREADS, LM_SMEM, stream>>>(wav, n_samples, wav_stride, w.dft_cos, w.dft_sin, w.hann,
+                                                            w.mel_start, w.mel_count, w.mel_weight, logspec, scratch_max);
+  TASTE_CUDA_OK(cudaGetLastError());
+  dim3 grid2(48, batch);
+  logmel_finish_kernel<<<grid2, 256, 0, stream>>>(logspec, scratch_max, feats_f32,
+                                                  static_cast<__nv_bfloat16*>(feats_bf16));
+  TASTE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace taste

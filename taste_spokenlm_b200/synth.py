@@ -138,9 +138,12 @@ def _randn(key: str, shape, seed: int) -> torch.Tensor:
 CODEBOOK_STD = 0.19     # minimises E min_j |r - c_j|^2 for r~N(0,I_256), 512 Gaussian codes (see module docstring)
 
 
-def random_weights(cfg: TowerConfig, seed: int = 1234) -> Dict[str, torch.Tensor]:
+def random_weights(cfg: TowerConfig, seed: int = 1234, only=None) -> Dict[str, torch.Tensor]:
+    """`only`: optional predicate on the key, to draw a subset (values do not depend on which keys are drawn)."""
     out: Dict[str, torch.Tensor] = OrderedDict()
     for key, shape in state_dict_spec(cfg).items():
+        if only is not None and not only(key):
+            continue
         r = None
         if key.endswith("embed_positions.weight") and key.startswith(ENC):
             r = sinusoids(shape[0], shape[1])
