@@ -147,6 +147,12 @@ int taste_encoder_fwd(taste_handle_t h, const float* feats_f32, const void* feat
                       void* h_target_bf16, void* ws, size_t ws_bytes, void* stream);
 
 /* --- R4/R5: token assembly (MT:144-152) + WhisperDecoder.forward with dict K/V (JES:377-388, CW:1200-1437) - */
+/* Token assembly (MT:144-152) on the device: asr_token_ids int64 [batch,tmax] (padded), token_lengths int32 [batch],
+ * cu_tokens int32 [batch+1] with cu[b+1]-cu[b] = T_b + 5  ->  tokens int32 packed [cu[batch]]:
+ * <sot>,<en>,<transcribe>,<notimestamps>, ids[b,:T_b], then the entry that follows in the reference's padded row
+ * (ids[b,T_b], or <eot> when T_b == tmax). */
+int taste_assemble_tokens(const int64_t* asr_token_ids, const int32_t* token_lengths, const int32_t* cu_tokens, int batch,
+                          int tmax, int32_t* tokens, void* stream);
 /* tokens: int32 packed [sum_tokens] assembled ids; cu_tokens: int32 [batch+1] row offsets.
  * dec_out: fp32 packed [sum_tokens, D] = decoder final LayerNorm state at every assembled position. */
 int taste_aggregator_fwd(taste_handle_t h, const void* h_last_bf16, const void* h_target_bf16, const int32_t* tokens,
@@ -192,6 +198,22 @@ int taste_layernorm_f32(const float* x, const float* w, const float* b, void* y,
 int taste_attention_bf16(const void* q, const void* k, const void* v, void* o, int ldq, int ldk, int ldv, int ldo,
                          const int32_t* cu_q, const int32_t* cu_kv, int q_len, int kv_len, int batch, int heads,
                          int causal, void* stream);
+
+/* --- instrumentation (no reference counterpart: SURVEY.md section 5 "tracing / profiling: none") ------------- */
+/* Kernels launched by this library in the calling process since load. */
+unsigned long long taste_launch_count(void);
+/* When enabled, every launch is bracketed by CUDA events on its own stream; taste_prof_collect() synchronises those
+ * events and returns one entry per kernel class that launched since the last taste_prof_reset(). */
+typedef struct {
+  const char* name;
+  long long   launches;
+  double      total_ms;   /* sum of per-launch device durations */
+  double      flops;      /* algorithmic FLOPs of those launches */
+  double      bytes;      /* algorithmic HBM bytes of those launches */
+} taste_prof_entry_t;
+int taste_prof_enable(int on);
+int taste_prof_reset(void);
+int taste_prof_collect(taste_prof_entry_t* out, int max_entries, int* n_out);
 
 #ifdef __cplusplus
 }

@@ -46,7 +46,16 @@ class Weights(C.Structure):
         "rvq_win_t", "rvq_bin", "rvq_code_t", "rvq_code", "rvq_code_sq", "rvq_wout_t", "rvq_bout")]
 
 
+class ProfEntry(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("launches", C.c_longlong), ("total_ms", C.c_double), ("flops", C.c_double),
+                ("bytes", C.c_double)]
+
+
 _SIGS = {
+    "taste_launch_count": (C.c_ulonglong, []),
+    "taste_prof_enable": (C.c_int, [C.c_int]),
+    "taste_prof_reset": (C.c_int, []),
+    "taste_prof_collect": (C.c_int, [C.POINTER(ProfEntry), C.c_int, C.POINTER(C.c_int)]),
     "taste_abi_version": (C.c_int, []),
     "taste_last_error": (C.c_char_p, []),
     "taste_handle_create": (C.c_int, [C.POINTER(Weights), C.POINTER(p)]),
@@ -55,6 +64,7 @@ _SIGS = {
     "taste_logmel_f32": (C.c_int, [p, p, p, C.c_int, C.c_int64, p, p, p, C.c_size_t, p]),
     "taste_encoder_fwd": (C.c_int, [p, p, p, C.c_int, p, p, p, C.c_size_t, p]),
     "taste_aggregator_fwd": (C.c_int, [p, p, p, p, p, C.c_int, C.c_int, C.c_int, p, p, C.c_size_t, p]),
+    "taste_assemble_tokens": (C.c_int, [p, p, p, C.c_int, C.c_int, p, p]),
     "taste_word_pool_f32": (C.c_int, [p, p, p, p, C.c_int, C.c_int, C.c_int, p, p]),
     "taste_rvq_encode_f32": (C.c_int, [p, p, p, C.c_int, C.c_int, C.c_int, p, p, p]),
     "taste_rvq_decode_f32": (C.c_int, [p, p, C.c_int, C.c_int, p, p]),
@@ -101,6 +111,16 @@ def check(rc: int, what: str = ""):
     if rc != 0:
         msg = load().taste_last_error().decode(errors="replace")
         raise TasteError(f"{what} failed (code {rc}): {msg}")
+
+
+def prof_collect():
+    """[{name, launches, total_ms, flops, bytes}] for every kernel class launched since the last taste_prof_reset()."""
+    lib = load()
+    arr = (ProfEntry * 32)()
+    n = C.c_int(0)
+    check(lib.taste_prof_collect(arr, 32, C.byref(n)), "taste_prof_collect")
+    return [dict(name=arr[i].name.decode(), launches=int(arr[i].launches), total_ms=float(arr[i].total_ms),
+                 flops=float(arr[i].flops), bytes=float(arr[i].bytes)) for i in range(n.value)]
 
 
 def ptr(t):

@@ -241,6 +241,7 @@ int taste_encoder_fwd(taste_handle_t h, const float* feats_f32, const void* feat
     at.batch = batch;
     at.heads = d.heads;
     at.causal = 0;
+    at.kclass = KC_ATTN_ENC;
     if ((rc = launch_attention(at, stream))) return rc;                                                      // CW:377-394
     if ((rc = gemm_plain(e.a, L.wo, L.bo, e.h, rows, D, D, EPI_RESID_F32, stream))) return rc;              // CW:407,692
     if ((rc = launch_layernorm(e.h, L.ln2_w, L.ln2_b, e.a, rows, D, true, stream))) return rc;              // CW:698
@@ -291,6 +292,8 @@ int taste_aggregator_fwd(taste_handle_t h, const void* h_last_bf16, const void* 
     at.batch = batch;
     at.heads = d.heads;
     at.causal = 1;
+    at.total_q = sum_tokens;
+    at.kclass = KC_ATTN_AGG;
     if ((rc = launch_attention(at, stream))) return rc;
     if ((rc = gemm_plain(g.att, L.wo, L.bo, g.d, rows, D, D, EPI_RESID_F32, stream))) return rc;
     // cross-attention: keys from the final encoder state, values from the layer-6 input, no mask        CW:361-366, 801-813
@@ -316,6 +319,12 @@ int taste_aggregator_fwd(taste_handle_t h, const void* h_last_bf16, const void* 
     if ((rc = gemm_plain(g.mid, L.w2, L.b2, g.d, rows, D, d.ffn, EPI_RESID_F32, stream))) return rc;
   }
   return launch_layernorm(g.d, w.dec_ln_w, w.dec_ln_b, dec_out, rows, D, false, stream);                    // CW:1415
+}
+
+int taste_assemble_tokens(const int64_t* asr_token_ids, const int32_t* token_lengths, const int32_t* cu_tokens, int batch,
+                          int tmax, int32_t* tokens, void* stream) {
+  return launch_assemble_tokens(asr_token_ids, token_lengths, cu_tokens, batch, tmax, tokens,
+                                static_cast<cudaStream_t>(stream));
 }
 
 int taste_word_pool_f32(const float* dec_out, const int32_t* cu_tokens, const int32_t* word_ids,

@@ -273,6 +273,10 @@ int launch_attention(const AttnDesc& d, cudaStream_t stream) {
   p.q_len = d.q_len; p.kv_len = d.kv_len;
   p.causal = d.causal;
   dim3 grid((d.q_len + ATT_BQ - 1) / ATT_BQ, d.heads, d.batch);
+  const double tq = d.total_q > 0 ? double(d.total_q) : double(d.batch) * d.q_len;
+  const double pairs = tq * d.kv_len * (d.causal ? 0.5 : 1.0);                  // causal: about half the tile
+  ProfScope ps(stream, d.kclass, 4.0 * pairs * ATT_HD * d.heads,
+               2.0 * ATT_HD * d.heads * (2.0 * tq + 2.0 * double(d.batch) * d.kv_len));
   attention_mma_kernel<<<grid, ATT_THREADS, 0, stream>>>(p);
   TASTE_CUDA_OK(cudaGetLastError());
   return 0;

@@ -72,6 +72,7 @@ int launch_layernorm(const float* x, const float* w, const float* b, void* y, in
   const int threads = 256;
   const int blocks = (rows + 7) / 8;
   const int vec = (d / 4 + 31) / 32;
+  ProfScope ps(stream, KC_LAYERNORM, 8.0 * rows * d, double(rows) * d * (4.0 + (out_bf16 ? 2.0 : 4.0)));
 #define TASTE_LN(V)                                                                           \
   do {                                                                                        \
     if (out_bf16) layernorm_kernel<V, true><<<blocks, threads, 0, stream>>>(x, w, b, y, rows, d);  \
@@ -108,7 +109,41 @@ int launch_cast_bf16(const float* x, void* y, int64_t n, cudaStream_t stream) {
   const int64_t n4 = n / 4;
   int blocks = int((n4 + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
+  ProfScope ps(stream, KC_CAST, 0.0, 6.0 * double(n));
   cast_bf16_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<uint2*>(y), n4);
+  TASTE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// token assembly (MT:144-152), packed: row b = prefix ++ ids[b, :T_b] ++ (ids[b, T_b] if T_b < Tmax else EOS).
+// The reference appends EOS after the PADDED width; by causality only the first T_b + 5 entries of a row can reach
+// the states the path consumes, and entry T_b + 4 is whatever sits there in the padded row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+assemble_tokens_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ lens, const int32_t* __restrict__ cu,
+                       int tmax, int32_t* __restrict__ tokens) {
+  const int b = blockIdx.x;
+  const int T = min(max(lens[b], 0), tmax);
+  const int base = cu[b];
+  for (int p = threadIdx.x; p < T + 5; p += blockDim.x) {
+    int32_t v;
+    if (p == 0) v = 50258;
+    else if (p == 1) v = 50259;
+    else if (p == 2) v = 50360;
+    else if (p == 3) v = 50364;
+    else if (p - 4 < tmax) v = int32_t(ids[int64_t(b) * tmax + p - 4]);
+    else v = 50257;
+    tokens[base + p] = v;
+  }
+}
+
+int launch_assemble_tokens(const int64_t* ids, const int32_t* lens, const int32_t* cu, int batch, int tmax,
+                           int32_t* tokens, cudaStream_t stream) {
+  if (!ids || !lens || !cu || !tokens) return set_error(TASTE_E_ARG, "assemble_tokens: null pointer");
+  if (batch <= 0) return 0;
+  ProfScope ps(stream, KC_EMBED, 0.0, 12.0 * double(batch) * (tmax + 5));
+  assemble_tokens_kernel<<<batch, 256, 0, stream>>>(ids, lens, cu, tmax, tokens);
   TASTE_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -146,6 +181,7 @@ int launch_embed(const int32_t* tokens, const int32_t* cu_tokens, int batch, int
                  const float* pos_emb, int d, int vocab, int max_pos, float* out, cudaStream_t stream) {
   if (sum_tokens <= 0) return 0;
   const int blocks = (sum_tokens + 7) / 8;
+  ProfScope ps(stream, KC_EMBED, double(sum_tokens) * d, 12.0 * double(sum_tokens) * d);
   embed_kernel<<<blocks, 256, 0, stream>>>(tokens, cu_tokens, batch, sum_tokens, tok_emb, pos_emb, d, vocab, max_pos, out);
   TASTE_CUDA_OK(cudaGetLastError());
   return 0;
@@ -200,6 +236,7 @@ int launch_word_pool(const float* dec_out, const int32_t* cu_tokens, const int32
   if (d % 4 != 0) return set_error(TASTE_E_SHAPE, "word_pool: d %% 4 != 0");
   if (batch <= 0 || tmax <= 0) return 0;
   dim3 grid(tmax, batch);
+  ProfScope ps(stream, KC_WORD_POOL, double(batch) * tmax * d, 8.0 * double(batch) * tmax * d);
   word_pool_kernel<<<grid, 256, 0, stream>>>(dec_out, cu_tokens, word_ids, token_lengths, tmax, d, z);
   TASTE_CUDA_OK(cudaGetLastError());
   return 0;
@@ -249,6 +286,7 @@ int launch_map_llm(const int64_t* asr_indices, const int32_t* asr_wid, const int
   if (nq > 8) return set_error(TASTE_E_SHAPE, "map_llm: num_q > 8");
   if (batch <= 0 || lmax <= 0) return 0;
   dim3 grid((lmax + 127) / 128, batch);
+  ProfScope ps(stream, KC_MAP_LLM, 0.0, 8.0 * double(batch) * (double(tmax) + lmax) * nq);
   map_llm_kernel<<<grid, 128, 0, stream>>>(asr_indices, asr_wid, asr_len, llm_wid, llm_len, tmax, lmax, nq, out);
   TASTE_CUDA_OK(cudaGetLastError());
   return 0;

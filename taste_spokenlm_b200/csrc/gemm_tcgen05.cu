@@ -287,6 +287,10 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
     configured = true;
   }
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  const double m = double(p.rows_out) * (p.total_tiles / (p.n_tiles * p.m_tiles_per_batch));
+  const double n = double(p.n_tiles) * BN, k = double(p.taps) * p.kb_per_tap * BK;
+  const double out_b = (EPI == EPI_BF16 || EPI == EPI_GELU_BF16) ? 2.0 : (EPI == EPI_RESID_F32 ? 8.0 : 4.0);
+  ProfScope ps(stream, KC_GEMM, 2.0 * m * n * k, 2.0 * (m * k / p.taps + n * k) + out_b * m * n);
   kern<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, stream>>>(ta, tb, p);
   TASTE_CUDA_OK(cudaGetLastError());
   return 0;

@@ -17,6 +17,20 @@ int set_error(int code, const char* fmt, ...);
     if (_e != cudaSuccess) return ::taste::set_error((int)_e, "%s: %s", #expr, cudaGetErrorString(_e)); \
   } while (0)
 
+// ---- launch accounting / device timing (prof.cu) ----
+enum KernelClass {
+  KC_GEMM = 0, KC_ATTN_ENC, KC_ATTN_AGG, KC_LAYERNORM, KC_CAST, KC_LOGMEL_TILE, KC_LOGMEL_FINISH, KC_EMBED,
+  KC_WORD_POOL, KC_RVQ_ENCODE, KC_RVQ_DECODE, KC_MAP_LLM, KC_ATTN_TC, KC_COUNT
+};
+// Wrap a kernel launch: counts it and, when profiling is on, brackets it with CUDA events on `stream`.
+// flops / bytes are the ALGORITHMIC work of the launch (DESIGN.md "Kernels").
+struct ProfScope {
+  ProfScope(cudaStream_t stream, int kc, double flops, double bytes);
+  ~ProfScope();
+  cudaStream_t stream_;
+  int slot_;
+};
+
 // ---- GEMM (gemm_tcgen05.cu) ----
 enum GemmEpilogue {
   EPI_BF16 = 0,          // out bf16 = acc + bias
@@ -61,6 +75,8 @@ struct AttnDesc {
   const int32_t* cu_kv;
   int q_len, kv_len;     // fixed lengths when cu_* is null; otherwise upper bounds used for the grid
   int batch, heads, causal;
+  int total_q = 0;       // sum of query rows (accounting only; 0 = batch * q_len)
+  int kclass = KC_ATTN_AGG;
 };
 int launch_attention(const AttnDesc& d, cudaStream_t stream);
 
@@ -68,6 +84,8 @@ int launch_attention(const AttnDesc& d, cudaStream_t stream);
 int launch_layernorm(const float* x, const float* w, const float* b, void* y, int rows, int d, bool out_bf16,
                      cudaStream_t stream);
 int launch_cast_bf16(const float* x, void* y, int64_t n, cudaStream_t stream);
+int launch_assemble_tokens(const int64_t* ids, const int32_t* lens, const int32_t* cu, int batch, int tmax,
+                           int32_t* tokens, cudaStream_t stream);
 int launch_embed(const int32_t* tokens, const int32_t* cu_tokens, int batch, int sum_tokens, const float* tok_emb,
                  const float* pos_emb, int d, int vocab, int max_pos, float* out, cudaStream_t stream);
 int launch_word_pool(const float* dec_out, const int32_t* cu_tokens, const int32_t* word_ids,

@@ -237,6 +237,10 @@ int launch_rvq_encode(const taste_weights_t& w, const float* z, const int32_t* l
   const int n_rows = batch * tmax;
   if (n_rows <= 0) return 0;
   const int blocks = (n_rows + RVQ_ROWS - 1) / RVQ_ROWS;
+  const double per_row = (in_dim == RVQ_DC ? 0.0 : 2.0 * in_dim * RVQ_DC) + w.dims.num_quantizers * 2.0 * RVQ_DC * RVQ_K +
+                         (quantized ? 2.0 * RVQ_DC * w.dims.d_model : 0.0);
+  ProfScope ps(stream, KC_RVQ_ENCODE, per_row * n_rows,
+               double(n_rows) * (4.0 * in_dim + 8.0 * w.dims.num_quantizers + (quantized ? 4.0 * w.dims.d_model : 0.0)));
   rvq_encode_kernel<<<blocks, RVQ_THREADS, 0, stream>>>(z, lengths, tmax, n_rows, in_dim, w.dims.d_model,
                                                         w.dims.num_quantizers, w.rvq_win_t, w.rvq_bin, w.rvq_code_t,
                                                         w.rvq_code, w.rvq_code_sq, w.rvq_wout_t, w.rvq_bout, indices,
@@ -251,6 +255,8 @@ int launch_rvq_decode(const taste_weights_t& w, const int64_t* indices, int n, b
   if (!indices || !out) return set_error(TASTE_E_ARG, "rvq_decode: null pointer");
   if (n <= 0) return 0;
   const int blocks = (n + RVQ_ROWS - 1) / RVQ_ROWS;
+  ProfScope ps(stream, KC_RVQ_DECODE, project_out ? 2.0 * RVQ_DC * w.dims.d_model * n : 0.0,
+               double(n) * (8.0 * w.dims.num_quantizers + 4.0 * (project_out ? w.dims.d_model : RVQ_DC)));
   rvq_decode_kernel<<<blocks, RVQ_THREADS, 0, stream>>>(indices, n, w.dims.num_quantizers, w.dims.d_model, w.rvq_code,
                                                         w.rvq_wout_t, w.rvq_bout, project_out ? 1 : 0, out);
   TASTE_CUDA_OK(cudaGetLastError());

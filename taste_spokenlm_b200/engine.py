@@ -287,18 +287,53 @@ class TowerEngine(FrontendEngine):
                                                  _lib.ptr(out), self._stream()), "taste_rvq_decode_f32")
         return out.reshape(*shape, out.shape[-1])
 
-    # ---- the whole tower: MT:108-211 --------------------------------------------------------------------------
-    def tower_forward(self, asr_token_ids, asr_token_lengths, audio_features, asr_word_ids, skip_vq: bool = False,
-                      lengths_host: Optional[np.ndarray] = None, ids_host: Optional[np.ndarray] = None):
+    def assemble_tokens(self, ids_dev: torch.Tensor, lens32: torch.Tensor, cu: torch.Tensor, sum_tokens: int):
+        """Packed assembled ids on the device (MT:144-152); see taste_assemble_tokens."""
+        B, Tmax = ids_dev.shape
+        tokens = torch.empty(sum_tokens, dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.taste_assemble_tokens(_lib.ptr(ids_dev), _lib.ptr(lens32), _lib.ptr(cu), B, Tmax,
+                                                  _lib.ptr(tokens), self._stream()), "taste_assemble_tokens")
+        return tokens
+
+    # ---- aggregator + pooling + RVQ on device-resident encoder states -------------------------------------------
+    def segment_and_quantize(self, h_last, h_t, ids_dev, wid_dev, lengths_host: np.ndarray, skip_vq: bool = False):
+        """MT:144-185 after the encoder: token assembly, aggregator, prefix skip + word pooling + EOS drop, RVQ.
+        `lengths_host` is the host copy of asr_token_lengths (the only host-side quantity the launch geometry needs)."""
         dev = self.device
-        B, Tmax = asr_token_ids.shape
-        if lengths_host is None:
-            lengths_host = asr_token_lengths.detach().cpu().numpy()
-        if ids_host is None:
-            ids_host = asr_token_ids.detach().cpu().numpy()
+        B, Tmax = ids_dev.shape
         lengths_host = np.asarray(lengths_host).astype(np.int64)
         if (lengths_host < 0).any() or (lengths_host > Tmax).any():
             raise ValueError("asr_token_lengths out of range")
+        cu_np = np.zeros(B + 1, dtype=np.int32)
+        cu_np[1:] = np.cumsum(lengths_host + 5)
+        meta = torch.from_numpy(np.concatenate([cu_np, lengths_host.astype(np.int32)])).to(dev, non_blocking=True)
+        cu, lens32 = meta[: B + 1], meta[B + 1:]
+        sum_tokens, max_tokens = int(cu_np[-1]), int(lengths_host.max()) + 5
+        tokens = self.assemble_tokens(ids_dev, lens32, cu, sum_tokens)
+        dec = self.aggregate(h_last, h_t, tokens, cu, sum_tokens, max_tokens)
+        z = self.word_pool(dec, cu, wid_dev, lens32, B, Tmax)
+        if skip_vq:                                                                      # MT:180,205
+            return z, None
+        Tm = int(lengths_host.max())             # generate_mask_from_length width (modules_taste/utils.py:5-8)
+        if Tm != Tmax:
+            raise ValueError(f"padded width {Tmax} != longest transcript {Tm}: the reference's mask/feature shapes "
+                             f"disagree in this case (MT:181-184)")
+        return self.rvq_encode(z, lens32)
+
+    # ---- waveform -> indices with everything resident on the device (corpus driver path) ------------------------
+    def tokenize_device(self, wav, n_samples, ids_dev, wid_dev, lengths_host, want_quantized: bool = True):
+        """wav fp32 [B, N] + n_samples int32 [B] + padded ids int64 / word ids int32 [B,Tmax], all on the device.
+        Returns (quantized [B,Tmax,D] fp32, indices [B,Tmax,Q] int64).  WF:87-113 -> MT:108-211."""
+        _, feats = self.logmel(wav, n_samples, want_f32=False, want_bf16=True)
+        h_last, h_t = self.encode(feats)
+        return self.segment_and_quantize(h_last, h_t, ids_dev, wid_dev, lengths_host)
+
+    # ---- the whole tower: MT:108-211 --------------------------------------------------------------------------
+    def tower_forward(self, asr_token_ids, asr_token_lengths, audio_features, asr_word_ids, skip_vq: bool = False,
+                      lengths_host: Optional[np.ndarray] = None):
+        dev = self.device
+        if lengths_host is None:
+            lengths_host = asr_token_lengths.detach().cpu().numpy()      # the reference syncs here too (MT:210)
         feats = audio_features
         if feats.shape[1] < _lib.N_FRAMES:                                              # JES:164-168
             feats = torch.nn.functional.pad(feats, (0, 0, 0, _lib.N_FRAMES - feats.shape[1]))
@@ -309,23 +344,10 @@ class TowerEngine(FrontendEngine):
             feats = feats.float()
         feats = feats.to(dev).contiguous()
         h_last, h_t = self.encode(feats)
-        tok_np, cu_np = self.assemble_tokens_host(ids_host, lengths_host)
-        tokens = torch.from_numpy(tok_np).to(dev, non_blocking=True)
-        cu = torch.from_numpy(cu_np).to(dev, non_blocking=True)
-        sum_tokens, max_tokens = int(cu_np[-1]), int(lengths_host.max()) + 5
-        dec = self.aggregate(h_last, h_t, tokens, cu, sum_tokens, max_tokens)
-        lens32 = torch.from_numpy(lengths_host.astype(np.int32)).to(dev, non_blocking=True)
+        ids = asr_token_ids.to(device=dev, dtype=torch.int64).contiguous()
         wid = asr_word_ids.to(device=dev, dtype=torch.int32).contiguous()
-        z = self.word_pool(dec, cu, wid, lens32, B, Tmax)
-        out = {"audio_unit_lengths": asr_token_lengths.clone()}
-        if skip_vq:                                                                      # MT:180,205
-            out["audio_unit_embeds"] = z
-            return out
-        Tm = int(lengths_host.max())             # generate_mask_from_length width (modules_taste/utils.py:5-8)
-        if Tm != Tmax:
-            raise ValueError(f"padded width {Tmax} != longest transcript {Tm}: the reference's mask/feature shapes "
-                             f"disagree in this case (MT:181-184)")
-        qz, idx = self.rvq_encode(z, lens32)
-        out["audio_unit_embeds"] = qz
-        out["quantized_indices"] = idx
+        qz, idx = self.segment_and_quantize(h_last, h_t, ids, wid, lengths_host, skip_vq=skip_vq)
+        out = {"audio_unit_lengths": asr_token_lengths.clone(), "audio_unit_embeds": qz}
+        if not skip_vq:
+            out["quantized_indices"] = idx
         return out

@@ -53,6 +53,8 @@ class WhisperFrontendB200(nn.Module):
         return super().to(*args, **kwargs)
 
     def engine(self, device=None) -> FrontendEngine:
+        if not torch.cuda.is_available():
+            raise _lib.TasteError("WhisperFrontendB200 needs a CUDA device (sm_100a); there is no CPU fallback")
         device = torch.device(device or self._device_hint or "cuda")
         if device.type == "cuda" and device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())

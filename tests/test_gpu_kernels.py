@@ -82,7 +82,7 @@ def test_gemm_rejects_bad_shapes(lib):
 # ---------------------------------------------------------------------------------------------------------------
 # LayerNorm
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("rows,d", [(1, 128), (37, 384), (3000, 1280), (5, 5120)])
+@pytest.mark.parametrize("rows,d", [(1, 128), (37, 384), (3000, 1280), (5, 2048)])
 @pytest.mark.parametrize("bf16", [0, 1])
 def test_layernorm(lib, rows, d, bf16):
     torch.manual_seed(rows + d)
@@ -261,8 +261,10 @@ def test_word_pool_vs_oracle_and_reference_cases(lib, golden_dir):
         torch.manual_seed(B * 31 + Tmax)
         dec = torch.randn(int(cu[-1]), D)
         z = torch.empty(B, Tmax, D, device="cuda")
-        _lib.check(lib.taste_word_pool_f32(_lib.ptr(dec.cuda()), _lib.ptr(cu.cuda()), _lib.ptr(wid.cuda()),
-                                           _lib.ptr(T.cuda()), B, Tmax, D, _lib.ptr(z), _stream()), "pool")
+        dec_d, cu_d, wid_d, T_d = dec.cuda(), cu.cuda(), wid.cuda(), T.cuda()      # keep the device copies alive
+        _lib.check(lib.taste_word_pool_f32(_lib.ptr(dec_d), _lib.ptr(cu_d), _lib.ptr(wid_d), _lib.ptr(T_d), B, Tmax, D,
+                                           _lib.ptr(z), _stream()), "pool")
+        torch.cuda.synchronize()
         # oracle on the padded [B, Tmax+1, D] view the reference sees (rows past T_b: whatever the decoder produced;
         # only row T_b can ever be pooled, and it exists in the packed layout)
         x = torch.zeros(B, Tmax + 1, D)
@@ -282,8 +284,8 @@ def test_map_to_llm_tokens(lib, golden_dir):
     B, T, Q = idx.shape
     L = z["llm_wid"].shape[1]
     out = torch.empty(B, L, Q, dtype=torch.int64, device="cuda")
-    a32 = lambda k: torch.from_numpy(z[k].astype(np.int32)).cuda()
-    _lib.check(lib.taste_map_to_llm_tokens(_lib.ptr(idx), _lib.ptr(a32("asr_wid")), _lib.ptr(a32("asr_len")),
-                                           _lib.ptr(a32("llm_wid")), _lib.ptr(a32("llm_len")), B, T, L, Q,
+    d = {k: torch.from_numpy(z[k].astype(np.int32)).cuda() for k in ("asr_wid", "asr_len", "llm_wid", "llm_len")}
+    _lib.check(lib.taste_map_to_llm_tokens(_lib.ptr(idx), _lib.ptr(d["asr_wid"]), _lib.ptr(d["asr_len"]),
+                                           _lib.ptr(d["llm_wid"]), _lib.ptr(d["llm_len"]), B, T, L, Q,
                                            _lib.ptr(out), _stream()), "map")
     assert np.array_equal(out.cpu().numpy(), z["llm_indices"])

@@ -1,0 +1,125 @@
+"""Host-side logic that needs no GPU: the C-ABI library loads and exports every declared symbol, the drop-in modules
+carry the reference's state_dict layout, the log-mel tables reproduce the DFT, and the product refuses to run on CPU."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import taste_oracle as O                      # checker only
+from taste_spokenlm_b200 import _lib, mel, synth
+
+torch.set_grad_enabled(False)
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    declared = _lib.declared_symbols()
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(built_lib, name), f"libtaste_b200.so does not export {name}"
+    assert set(declared) == set(_lib._SIGS), "ctypes signature table out of sync with include/taste_b200.h"
+    assert built_lib.taste_abi_version() == 1
+    assert isinstance(built_lib.taste_launch_count(), int)
+
+
+def test_argument_errors_without_a_gpu(built_lib):
+    # argument validation happens before any CUDA call, so these are safe on a CPU box
+    assert built_lib.taste_handle_create(None, None) == -1
+    assert b"null" in built_lib.taste_last_error()
+    assert built_lib.taste_gemm_bf16(None, None, None, None, 1, 128, 64, 9, None) == -1
+    assert built_lib.taste_ws_bytes(None, 4, 100) == 0
+
+
+def test_tower_module_state_layout_matches_reference_keys():
+    from taste_spokenlm_b200.tower import TasteAudioTowerB200
+    for cfg in (synth.TINY, synth.SMALL):
+        t = TasteAudioTowerB200.from_config(cfg)
+        sd = t.state_dict()
+        spec = synth.state_dict_spec(cfg)
+        assert list(sd.keys()) == list(spec.keys()) or set(sd.keys()) == set(spec.keys())
+        for k, shape in spec.items():
+            assert tuple(sd[k].shape) == tuple(shape), k
+        # identity cross-attention v_proj at construction (JES:320-322)
+        v = sd["audio_joint_encoder_segmenter.audio_segmenter.decoder.layers.0.encoder_attn.v_proj.weight"]
+        assert torch.equal(v, torch.eye(cfg.d_model))
+        t.load_state_dict(synth.random_weights(cfg, 3), strict=True)
+
+
+def test_full_size_spec_matches_golden_reference_key_list(golden_dir):
+    # the 759.0 M parameter count of SURVEY section 6 (audio tower incl. RVQ and the unused QINCo MLPs)
+    spec = synth.state_dict_spec(synth.FULL)
+    n = sum(int(np.prod(s)) for k, s in spec.items()
+            if not any(k.endswith(b) for b in ("initted", "cluster_size", "embed_avg", "_codebook.embed")))
+    assert abs(n / 1e6 - 759.0) < 1.0, n / 1e6
+
+
+def test_product_has_no_cpu_fallback():
+    from taste_spokenlm_b200.tower import TasteAudioTowerB200
+    from taste_spokenlm_b200.frontend import WhisperFrontendB200
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    t = TasteAudioTowerB200.from_config(synth.TINY).eval()
+    b = synth.synth_batch(0, [1.0], [4])
+    with pytest.raises(_lib.TasteError):
+        t(b["asr_token_ids"], b["asr_token_lengths"], torch.zeros(1, 3000, 128), torch.tensor([3000]),
+          asr_word_ids=b["asr_word_ids"])
+    with pytest.raises(_lib.TasteError):
+        WhisperFrontendB200(whisper_model="large-v3", permute=True)(b["wav"], b["n_samples"])
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "taste_spokenlm_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_token_assembly_host_matches_oracle():
+    from taste_spokenlm_b200.engine import TowerEngine
+    ids = torch.tensor([[5, 6, 7, 8], [9, 10, 0, 0], [11, 0, 0, 0]])
+    lens = np.array([4, 2, 1])
+    tok, cu = TowerEngine.assemble_tokens_host(ids.numpy(), lens)
+    full = O.assemble_tokens(ids)                                      # MT:144-151, padded
+    for b in range(3):
+        assert tok[cu[b]:cu[b + 1]].tolist() == full[b, : lens[b] + 5].tolist()
+    assert cu.tolist() == [0, 9, 16, 22]
+
+
+def test_mel_tables_match_oracle_filterbank():
+    fb = mel.slaney_filterbank()
+    np.testing.assert_allclose(fb, O.mel_filterbank(), rtol=2e-6, atol=1e-9)
+    st, cnt, wt = mel.sparse_filterbank()
+    dense = np.zeros_like(fb)
+    for m in range(128):
+        dense[m, st[m]: st[m] + cnt[m]] = wt[m, : cnt[m]]
+    assert np.array_equal(dense, fb)
+    assert int(cnt.sum()) >= 394 and int(np.count_nonzero(fb)) == 394
+
+
+def test_folded_dft_tables_reproduce_rfft():
+    """The kernel's arithmetic (logmel.cu stage 1-2) in numpy fp64: X[k] = sum_{n=1..199} E[n] cos - i O[n] sin
+    + (-1)^k y[200], with E/O the folded windowed frame; must equal rfft(frame * hann)."""
+    c, s = mel.dft_tables()
+    w = mel.hann_periodic().astype(np.float64)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(400)
+    y = w * x
+    n = np.arange(1, 200)
+    E = y[n] + y[400 - n]
+    Od = y[n] - y[400 - n]
+    k = np.arange(201)
+    re = E @ c[:199, :201].astype(np.float64) + np.where(k % 2 == 1, -1.0, 1.0) * y[200]      # y[0] = 0 (periodic Hann)
+    im = Od @ s[:199, :201].astype(np.float64)
+    ref = np.fft.rfft(y)
+    np.testing.assert_allclose(re, ref.real, atol=2e-5)
+    np.testing.assert_allclose(im, -ref.imag, atol=2e-5)
+    assert w[0] == 0.0
+
+
+def test_word_runs_padded_row_quirk():
+    # a final word with id 0 merges with the zero padding and is not pooled
+    assert O.word_runs(torch.tensor([0, 0, 0, 0]), 2) == []
+    assert O.word_runs(torch.tensor([0, 0]), 2) == [(0, 2)]
+    assert O.word_runs(torch.tensor([0, 1, 1, 2, 2, 2, 0, 0]), 7) == [(1, 3), (3, 6)]
