@@ -189,6 +189,9 @@ int taste_map_to_llm_tokens(const int64_t* asr_indices, const int32_t* asr_word_
  * 3 = fp32 out.  Requires N % 128 == 0, K % 64 == 0. */
 int taste_gemm_bf16(const void* a, const void* w, const float* bias, void* out, int m, int n, int k, int epilogue,
                     void* stream);
+/* Tile-shape override for A/B timing and tests: 0 = automatic (CTA pairs, 256 x 256 tiles, when one wave of pair tiles
+ * exists), 1 = always the single-CTA 128 x {256,128} kernel.  Process-wide. */
+int taste_gemm_set_mode(int mode);
 /* y = LayerNorm(x) (eps 1e-5, CW:660): x fp32 [rows, d]; y bf16 (out_bf16 != 0) or fp32. */
 int taste_layernorm_f32(const float* x, const float* w, const float* b, void* y, int rows, int d, int out_bf16,
                         void* stream);

@@ -122,6 +122,74 @@ TASTE_DEVINL void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------
+// CTA pairs (cta_group::2): cluster rank, peer addresses, remote barrier arrives, 2-SM TMA / MMA / commit
+// ------------------------------------------------------------------------------------------------
+TASTE_DEVINL uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+TASTE_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `smem_addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+TASTE_DEVINL uint32_t mapa_shared(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+TASTE_DEVINL void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes)
+               : "memory");
+}
+TASTE_DEVINL void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads whose completion bytes are signalled on a barrier of the PAIR LEADER (cluster address)
+TASTE_DEVINL void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+TASTE_DEVINL void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1, int c2,
+                                  int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+      "%5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+TASTE_DEVINL void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {   // one full warp in EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+}
+TASTE_DEVINL void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+TASTE_DEVINL void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem, 128 rows per CTA] * B[smem, N/2 rows per CTA]; issued by the leader CTA only
+TASTE_DEVINL void umma_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this smem offset in every CTA of `cta_mask` once all prior MMAs of this thread retire
+TASTE_DEVINL void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+
 // K-major, 128-byte-swizzled operand tile (rows of 64 bf16 = 128 B, 8-row swizzle atoms 1024 B apart).
 // Field layout follows the sm_100 shared-memory matrix descriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
 // version=1 [46,48), layout type [61,64) (2 = SWIZZLE_128B).
@@ -171,16 +239,26 @@ TASTE_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;"
 // ------------------------------------------------------------------------------------------------
 // math
 // ------------------------------------------------------------------------------------------------
-// erf to ~1.5e-7 absolute (Abramowitz & Stegun 7.1.26): one ex2, one rcp, 6 FMA.  Far below bf16 resolution.
+TASTE_DEVINL float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+TASTE_DEVINL float fast_exp2_(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// erf to ~2e-7 absolute (Abramowitz & Stegun 7.1.26): two MUFU (rcp, ex2) + 9 FMA-pipe ops.  Far below bf16 resolution.
 TASTE_DEVINL float fast_erf(float x) {
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float t = fast_rcp(fmaf(0.3275911f, ax, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
   p *= t;
-  const float e = __expf(-ax * ax);
+  const float e = fast_exp2_((ax * -1.4426950408889634f) * ax);
   const float r = fmaf(-p, e, 1.0f);
   return copysignf(r, x);
 }
@@ -188,7 +266,8 @@ TASTE_DEVINL float fast_erf(float x) {
 template <bool kFast>
 TASTE_DEVINL float gelu_erf(float x) {
   const float e = kFast ? fast_erf(x * 0.70710678118654752f) : erff(x * 0.70710678118654752f);
-  return 0.5f * x * (1.0f + e);
+  const float hx = 0.5f * x;
+  return fmaf(hx, e, hx);
 }
 
 TASTE_DEVINL float fast_exp2(float x) {

@@ -8,6 +8,7 @@
 // Roles (256 threads, 1 CTA / SM):  warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
 // warps 4-7 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31 = rows of the 128-row tile).
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "internal.h"
@@ -247,6 +248,178 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): one 256 x 256 output tile per pair of SMs.  Each CTA stages its own 128 rows of A
+// and 128 of the 256 B rows per k-block (32 KB instead of the 48 KB a single-CTA 128 x 256 tile needs), which is
+// what lifts the kernel off the L2 -> SM bandwidth ceiling.  The leader CTA issues the MMAs for both; accumulators
+// (128 lanes x 256 columns per CTA, double buffered) live in each CTA's own TMEM.
+// Roles per CTA (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (leader only), warp 2 = TMEM allocator,
+// warps 4-11 = epilogue (warp w: TMEM lanes 32*(w%4)..+31, columns 128*((w-4)/4)..+127).
+// ------------------------------------------------------------------------------------------------
+constexpr int kGemm2Threads = 384;
+constexpr int BN2 = 256;
+struct Gemm2Cfg {
+  static constexpr int kStages = 6;
+  static constexpr uint32_t kABytes = BM * BK * 2;           // this CTA's 128 rows of A
+  static constexpr uint32_t kBBytes = (BN2 / 2) * BK * 2;    // this CTA's 128 of the 256 B rows
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr uint32_t kTmemCols = 2 * BN2;
+  static constexpr size_t kSmemBytes = 1024 + size_t(kStages) * kStageBytes + 256;
+};
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
+gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                              const GemmParams p) {
+  using Cfg = Gemm2Cfg;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + size_t(kStages) * Cfg::kStageBytes);   // used in the leader
+  uint64_t* empty_bar = full_bar + kStages;    // per CTA: smem slot free (MMA commit, multicast to both CTAs)
+  uint64_t* tfull_bar = empty_bar + kStages;   // per CTA: accumulator ready (MMA commit, multicast)
+  uint64_t* tempty_bar = tfull_bar + 2;        // leader: accumulator drained by the 16 epilogue warps of the pair
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int n_pairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);            // the leader's arrive.expect_tx covers the bytes of both CTAs
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 16);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int kb_total = p.taps * p.kb_per_tap;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer (both CTAs) =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < p.total_tiles; tile += n_pairs) {
+        const int nt = tile % p.n_tiles;
+        const int mg = tile / p.n_tiles;
+        const int b = mg / p.m_tiles_per_batch;
+        const int mt = mg - b * p.m_tiles_per_batch;
+        const int row0 = mt * (2 * BM) + int(rank) * BM;
+        const int col0 = nt * BN2 + int(rank) * (BN2 / 2);
+        for (int kb = 0; kb < kb_total; ++kb) {
+          const int tap = kb / p.kb_per_tap;
+          const int kc = kb - tap * p.kb_per_tap;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + size_t(stage) * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          // Both CTAs' TMA bytes are counted on the LEADER's barrier; only the leader arrives (expecting both halves).
+          // The peer cannot run a phase ahead: its slot is released by the same multicast commit as the leader's.
+          const uint32_t lead_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          const int ts = tap == 0 ? p.tap_s[0] : (tap == 1 ? p.tap_s[1] : p.tap_s[2]);
+          const int tr = tap == 0 ? p.tap_dr[0] : (tap == 1 ? p.tap_dr[1] : p.tap_dr[2]);
+          tma_load_4d_2sm(sa, &tma_a, lead_full, kc * BK, ts, row0 + tr, b);
+          tma_load_2d_2sm(sb, &tma_b, lead_full, kb * BK, col0);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      // ===================== MMA issuer (leader CTA only) =====================
+      constexpr uint32_t idesc = umma_idesc(2 * BM, BN2, /*bf16*/ 1, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = pair; tile < p.total_tiles; tile += n_pairs) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(as * BN2);
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + size_t(stage) * Cfg::kStageBytes);
+          const uint64_t da = umma_desc_k_sw128(sa);
+          const uint64_t db = umma_desc_k_sw128(sa + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_ss_2sm(d_tmem, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[stage], 0x3);    // both CTAs may refill this slot once the MMAs retire
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&tfull_bar[as], 0x3);
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs) =====================
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    int as = 0;
+    uint32_t aphase = 0;
+    const uint32_t lead_tempty0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
+    const uint32_t lead_tempty1 = mapa_shared(smem_u32(&tempty_bar[1]), 0);
+    for (int tile = pair; tile < p.total_tiles; tile += n_pairs) {
+      const int nt = tile % p.n_tiles;
+      const int mg = tile / p.n_tiles;
+      const int b = mg / p.m_tiles_per_batch;
+      const int mt = mg - b * p.m_tiles_per_batch;
+      const int row_in_batch = mt * (2 * BM) + int(rank) * BM + q * 32 + lane;
+      const bool valid = row_in_batch < p.rows_out;
+      const int64_t grow = int64_t(b) * p.rows_out + row_in_batch;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN2 + half * (BN2 / 2));
+#pragma unroll 1
+      for (int c = 0; c < BN2 / 64; ++c) {
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(taddr + uint32_t(c * 32), acc);
+        tmem_ld_wait();
+        if (valid) epilogue_chunk<EPI>(acc, p, grow, row_in_batch, nt * BN2 + half * (BN2 / 2) + c * 32);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(as == 0 ? lead_tempty0 : lead_tempty1);
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();          // the peer's remote arrives and smem reads are complete before either CTA exits
+  if (warp == 2) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -296,6 +469,50 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
   return 0;
 }
 
+template <int EPI>
+static int launch_cfg2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  auto kern = gemm_bf16_tcgen05_2cta_kernel<EPI>;
+  static int max_pairs = 0;
+  if (max_pairs == 0) {
+    TASTE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gemm2Cfg::kSmemBytes));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * num_sms());
+    cfg.blockDim = dim3(kGemm2Threads);
+    cfg.dynamicSmemBytes = Gemm2Cfg::kSmemBytes;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    TASTE_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    if (n <= 0) return set_error(TASTE_E_NO_DEVICE, "gemm: no CTA pair fits on this device");
+    max_pairs = n;
+    if (getenv("TASTE_DEBUG")) fprintf(stderr, "[taste] gemm pair kernel: %d co-resident CTA pairs\n", n);
+  }
+  const int pairs = p.total_tiles < max_pairs ? p.total_tiles : max_pairs;
+  const double m = double(p.rows_out) * (p.total_tiles / (p.n_tiles * p.m_tiles_per_batch));
+  const double n = double(p.n_tiles) * BN2, k = double(p.taps) * p.kb_per_tap * BK;
+  const double out_b = (EPI == EPI_BF16 || EPI == EPI_GELU_BF16) ? 2.0 : (EPI == EPI_RESID_F32 ? 8.0 : 4.0);
+  ProfScope ps(stream, KC_GEMM, 2.0 * m * n * k, 2.0 * (m * k / p.taps + n * k) + out_b * m * n);
+  kern<<<2 * pairs, kGemm2Threads, Gemm2Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  TASTE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int launch_epi2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int epi, cudaStream_t s) {
+  switch (epi) {
+    case EPI_BF16: return launch_cfg2<EPI_BF16>(ta, tb, p, s);
+    case EPI_GELU_BF16: return launch_cfg2<EPI_GELU_BF16>(ta, tb, p, s);
+    case EPI_RESID_F32: return launch_cfg2<EPI_RESID_F32>(ta, tb, p, s);
+    case EPI_F32: return launch_cfg2<EPI_F32>(ta, tb, p, s);
+    case EPI_GELU_POS_F32: return launch_cfg2<EPI_GELU_POS_F32>(ta, tb, p, s);
+  }
+  return set_error(TASTE_E_ARG, "gemm: unknown epilogue %d", epi);
+}
+
 template <int BN>
 static int launch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int epi, cudaStream_t s) {
   switch (epi) {
@@ -308,6 +525,10 @@ static int launch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
   return set_error(TASTE_E_ARG, "gemm: unknown epilogue %d", epi);
 }
 
+// 0 = automatic, 1 = force the single-CTA kernel (tests / A-B timing)
+static int g_gemm_mode = 0;
+void set_gemm_mode(int mode) { g_gemm_mode = mode; }
+
 int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
   if (!d.a || !d.w || !d.out) return set_error(TASTE_E_ARG, "gemm: null pointer");
   if (d.k_inner % BK != 0 || d.n % 128 != 0 || d.taps < 1 || d.taps > 3)
@@ -318,9 +539,12 @@ int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return set_error(TASTE_E_NO_DEVICE, "cuTensorMapEncodeTiled entry point unavailable");
 
-  const int m_tiles = (d.rows_out + BM - 1) / BM;
+  // tile shape: CTA pairs (256 x 256) when there is at least one wave of pair tiles, else single-CTA 128 x {256,128}
+  const int64_t pair_tiles = (d.n % 256 == 0) ? int64_t((d.rows_out + 2 * BM - 1) / (2 * BM)) * d.batches * (d.n / 256) : 0;
+  const bool use_pair = g_gemm_mode != 1 && pair_tiles >= num_sms() / 2;
+  const int m_tiles = use_pair ? (d.rows_out + 2 * BM - 1) / (2 * BM) : (d.rows_out + BM - 1) / BM;
   const int64_t tiles256 = (d.n % 256 == 0) ? int64_t(m_tiles) * d.batches * (d.n / 256) : 0;
-  const int bn = (tiles256 >= num_sms()) ? 256 : 128;
+  const int bn = use_pair ? 128 /* B box: this CTA's half of the 256 columns */ : ((tiles256 >= num_sms()) ? 256 : 128);
 
   CUtensorMap ta, tb;
   {
@@ -347,7 +571,7 @@ int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
   GemmParams p;
   p.rows_out = d.rows_out;
   p.m_tiles_per_batch = m_tiles;
-  p.n_tiles = d.n / bn;
+  p.n_tiles = use_pair ? d.n / 256 : d.n / bn;
   p.total_tiles = m_tiles * d.batches * p.n_tiles;
   p.kb_per_tap = d.k_inner / BK;
   p.taps = d.taps;
@@ -359,6 +583,7 @@ int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
   p.out = d.out;
   p.ldc = d.ldc;
   p.pos = d.pos;
+  if (use_pair) return launch_epi2(ta, tb, p, d.epilogue, stream);
   return bn == 256 ? launch_epi<256>(ta, tb, p, d.epilogue, stream) : launch_epi<128>(ta, tb, p, d.epilogue, stream);
 }
 

@@ -63,6 +63,7 @@ struct GemmDesc {
   const float* pos = nullptr;
 };
 int launch_gemm(const GemmDesc& d, cudaStream_t stream);
+void set_gemm_mode(int mode);
 int gemm_plain(const void* a, const void* w, const float* bias, void* out, int m, int n, int k, int epilogue,
                cudaStream_t stream);
 

@@ -44,9 +44,15 @@ def rvq_engine(lib):
 # GEMM (tcgen05)
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("m,n,k", [(128, 128, 64), (256, 256, 128), (1500, 1280, 1280), (35, 384, 128),
-                                   (3000, 3840, 1280), (777, 5120, 1280), (20000, 1280, 5120), (129, 256, 192)])
+                                   (3000, 3840, 1280), (777, 5120, 1280), (20000, 1280, 5120), (129, 256, 192),
+                                   (19000, 256, 64), (9601, 2560, 320)])
 @pytest.mark.parametrize("epi", [0, 1, 2, 3])
-def test_gemm(lib, m, n, k, epi):
+@pytest.mark.parametrize("mode", [0, 1])
+def test_gemm(lib, m, n, k, epi, mode):
+    """mode 0: automatic tile shape (CTA pairs for the large cases); mode 1: single-CTA kernel everywhere."""
+    if mode == 1 and m < 3000:
+        pytest.skip("small shapes already use the single-CTA kernel in mode 0")
+    assert lib.taste_gemm_set_mode(mode) == 0
     torch.manual_seed(m * 7 + n * 3 + k + epi)
     a = (torch.randn(m, k, device="cuda") * 0.5).bfloat16()
     w = (torch.randn(n, k, device="cuda") / math.sqrt(k)).bfloat16()
@@ -65,6 +71,7 @@ def test_gemm(lib, m, n, k, epi):
     _lib.check(lib.taste_gemm_bf16(_lib.ptr(a), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(out), m, n, k, epi, _stream()),
                "gemm")
     torch.cuda.synchronize()
+    lib.taste_gemm_set_mode(0)
     assert torch.isfinite(out.float()).all()
     tol = 4e-3 if epi in (0, 1) else 2e-5 * math.sqrt(k)       # bf16 output rounding vs fp32 accumulate-order noise
     assert _rel(out.float(), ref) < tol
