@@ -218,6 +218,10 @@ int taste_prof_enable(int on);
 int taste_prof_reset(void);
 int taste_prof_collect(taste_prof_entry_t* out, int max_entries, int* n_out);
 
+/* Kernel override for A/B timing and tests: 0 = automatic (tcgen05/TMEM kernel for fixed-length non-causal problems
+ * with >= 256 queries, mma.sync kernel for the ragged / causal aggregator shapes), 1 = always the mma.sync kernel. */
+int taste_attention_set_mode(int mode);
+
 #ifdef __cplusplus
 }
 #endif

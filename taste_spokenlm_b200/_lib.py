@@ -70,6 +70,7 @@ _SIGS = {
     "taste_rvq_decode_f32": (C.c_int, [p, p, C.c_int, C.c_int, p, p]),
     "taste_map_to_llm_tokens": (C.c_int, [p, p, p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, p, p]),
     "taste_gemm_bf16": (C.c_int, [p, p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, p]),
+    "taste_attention_set_mode": (C.c_int, [C.c_int]),
     "taste_gemm_set_mode": (C.c_int, [C.c_int]),
     "taste_layernorm_f32": (C.c_int, [p, p, p, p, C.c_int, C.c_int, C.c_int, p]),
     "taste_attention_bf16": (C.c_int, [p, p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, p, p, C.c_int, C.c_int,

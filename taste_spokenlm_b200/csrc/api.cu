@@ -357,6 +357,12 @@ int taste_gemm_bf16(const void* a, const void* w, const float* bias, void* out, 
   return gemm_plain(a, w, bias, out, m, n, k, epilogue, static_cast<cudaStream_t>(stream));
 }
 
+int taste_attention_set_mode(int mode) {
+  if (mode < 0 || mode > 1) return set_error(TASTE_E_ARG, "attention_set_mode: mode must be 0 or 1");
+  set_attention_mode(mode);
+  return 0;
+}
+
 int taste_gemm_set_mode(int mode) {
   if (mode < 0 || mode > 1) return set_error(TASTE_E_ARG, "gemm_set_mode: mode must be 0 or 1");
   set_gemm_mode(mode);

@@ -258,9 +258,13 @@ attention_mma_kernel(const AttnParams p) {
   }
 }
 
+static int g_attn_mode = 0;
+void set_attention_mode(int mode) { g_attn_mode = mode; }
+
 int launch_attention(const AttnDesc& d, cudaStream_t stream) {
   if (!d.q || !d.k || !d.v || !d.o) return set_error(TASTE_E_ARG, "attention: null pointer");
   if (d.batch <= 0 || d.heads <= 0 || d.q_len <= 0 || d.kv_len <= 0) return 0;
+  if (g_attn_mode == 0 && attention_tcgen05_eligible(d)) return launch_attention_tcgen05(d, stream);
   if ((d.ldq | d.ldk | d.ldv) % 8 != 0 || d.ldo % 2 != 0)
     return set_error(TASTE_E_SHAPE, "attention: row strides must be multiples of 8 elements");
   AttnParams p;

@@ -1,0 +1,340 @@
+// Non-causal flash attention on the 5th-generation tensor cores (tcgen05 + TMEM), head_dim 64, bf16 in / out, fp32
+// scores and accumulators.  Serves the encoder self-attention (CW:377-394 eager semantics: softmax(q k^T) v with q
+// pre-scaled, NO mask — JES:198-203), which is 16 % of the path's FLOPs.
+//
+// One CTA owns 256 queries of one (utterance, head) as two 128-row tiles that ping-pong through the tensor pipe:
+//   S_i = Q_i K_j^T   tcgen05.mma  SS  (M 128, N 128 keys, K 64)      -> TMEM, 128 fp32 columns per tile
+//   softmax           one thread per query row reads its S row with tcgen05.ld (no shuffles), keeps the running
+//                     max / sum in registers, writes P (bf16) back to TMEM with tcgen05.st
+//   O_i += P_i V_j    tcgen05.mma  TS  (A = P from TMEM, B = V tile, MN-major; M 128, N 64, K 128 keys)
+// While warpgroup i exponentiates, the MMA warp runs the other tile's GEMMs.  K/V tiles arrive by TMA (128-byte
+// swizzle) through a 4-stage mbarrier ring straight from the packed [rows, 3*D] QKV activation.  The accumulator is
+// rescaled only when a row's maximum grows by more than 2^8 (the stale maximum keeps exp2 arguments <= 8, exact in
+// fp32 / bf16 range), so the O read-modify-write in TMEM is rare after the first key block.
+//
+// Roles (320 threads): warps 0-3 softmax tile 0, warps 4-7 softmax tile 1 (warp w owns TMEM lanes 32*(w%4)..+31),
+// warp 8 TMA producer, warp 9 MMA issuer + TMEM allocator.
+#include "common.cuh"
+#include "internal.h"
+
+namespace taste {
+
+constexpr int FA_BQ = 128;          // query rows per tile (2 tiles per CTA)
+constexpr int FA_BK = 128;          // keys per block
+constexpr int FA_HD = 64;
+constexpr int FA_STAGES = 4;
+constexpr int FA_THREADS = 320;
+constexpr uint32_t FA_TILE_BYTES = FA_BQ * FA_HD * 2;      // 16 KB: one Q, K or V tile
+constexpr size_t FA_SMEM = 1024 + size_t(2 + 2 * FA_STAGES) * FA_TILE_BYTES + 256;
+
+// TMEM columns
+constexpr uint32_t FA_COL_S = 0;      // S0 [0,128)  S1 [128,256)
+constexpr uint32_t FA_COL_O = 256;    // O0 [256,320) O1 [320,384)
+constexpr uint32_t FA_COL_P = 384;    // P0 [384,448) P1 [448,512)   (bf16 pairs: 64 columns per 128 keys)
+
+struct FaParams {
+  __nv_bfloat16* o;
+  int ldo;
+  int q_len, kv_len;
+};
+
+__global__ void __launch_bounds__(FA_THREADS, 1)
+attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                         const __grid_constant__ CUtensorMap tma_v, const FaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                   // 2 tiles
+  uint8_t* sKV = smem + 2 * FA_TILE_BYTES;              // FA_STAGES x {K, V}
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + size_t(2 * FA_STAGES) * FA_TILE_BYTES);
+  uint64_t* q_full = bars;                              // [1]
+  uint64_t* kv_full = bars + 1;                         // [FA_STAGES]
+  uint64_t* kv_empty = kv_full + FA_STAGES;             // [FA_STAGES]
+  uint64_t* s_full = kv_empty + FA_STAGES;              // [2]  S_i ready            (MMA -> softmax)
+  uint64_t* p_full = s_full + 2;                        // [2]  P_i written, S_i free (softmax -> MMA), 4 warp arrivals
+  uint64_t* o_full = p_full + 2;                        // [2]  P_i V done           (MMA -> softmax)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.z;
+  const int head = blockIdx.y;
+  const int q0 = blockIdx.x * (2 * FA_BQ);
+  const int n_blocks = (p.kv_len + FA_BK - 1) / FA_BK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tma_q);
+    tma_prefetch_desc(&tma_k);
+    tma_prefetch_desc(&tma_v);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < FA_STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 9) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      mbar_expect_tx(q_full, 2 * FA_TILE_BYTES);
+      tma_load_3d(sQ, &tma_q, q_full, head * FA_HD, q0, b);
+      tma_load_3d(sQ + FA_TILE_BYTES, &tma_q, q_full, head * FA_HD, q0 + FA_BQ, b);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_blocks; ++j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        uint8_t* sk = sKV + size_t(2 * stage) * FA_TILE_BYTES;
+        mbar_expect_tx(&kv_full[stage], 2 * FA_TILE_BYTES);
+        tma_load_3d(sk, &tma_k, &kv_full[stage], head * FA_HD, j * FA_BK, b);
+        tma_load_3d(sk + FA_TILE_BYTES, &tma_v, &kv_full[stage], head * FA_HD, j * FA_BK, b);
+        if (++stage == FA_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc_qk = umma_idesc(FA_BQ, FA_BK, 1, 0, 0);        // A, B K-major
+      constexpr uint32_t idesc_pv = umma_idesc(FA_BQ, FA_HD, 1, 0, 1);        // A from TMEM, B (V) MN-major
+      auto issue_qk = [&](int i, int stage) {
+        const uint64_t da = umma_desc_k_sw128(smem_u32(sQ + size_t(i) * FA_TILE_BYTES));
+        const uint64_t db = umma_desc_k_sw128(smem_u32(sKV + size_t(2 * stage) * FA_TILE_BYTES));
+#pragma unroll
+        for (int k = 0; k < FA_HD / 16; ++k)
+          umma_ss(tmem_base + FA_COL_S + uint32_t(i * FA_BK), da + uint64_t(k * 2), db + uint64_t(k * 2), idesc_qk,
+                  k != 0 ? 1u : 0u);
+        umma_commit(&s_full[i]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_qk(0, 0);
+      issue_qk(1, 0);
+      int stage = 0;
+      uint32_t phase = 0;          // phase of kv_full[stage] for block j
+      for (int j = 0; j < n_blocks; ++j) {
+        int nstage = stage + 1;
+        uint32_t nphase = phase;
+        if (nstage == FA_STAGES) {
+          nstage = 0;
+          nphase ^= 1;
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          mbar_wait(&p_full[i], uint32_t(j & 1));
+          tc_fence_after();
+          if (j + 1 < n_blocks) {
+            if (i == 0) {
+              mbar_wait(&kv_full[nstage], nphase);
+              tc_fence_after();
+            }
+            issue_qk(i, nstage);                 // next block's scores first: the softmax warps wait on these
+          }
+          const uint64_t dv = umma_desc_mn_sw128(smem_u32(sKV + size_t(2 * stage + 1) * FA_TILE_BYTES), 0);
+#pragma unroll
+          for (int k = 0; k < FA_BK / 16; ++k)     // 16 keys per MMA: 8 TMEM columns of P, 2048 B of V
+            umma_ts(tmem_base + FA_COL_O + uint32_t(i * FA_HD), tmem_base + FA_COL_P + uint32_t(i * 64 + k * 8),
+                    dv + uint64_t(k * (2048 >> 4)), idesc_pv, (j | k) != 0 ? 1u : 0u);
+          umma_commit(&o_full[i]);
+          if (i == 1) umma_commit(&kv_empty[stage]);
+        }
+        stage = nstage;
+        phase = nphase;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax + output (warps 0-7) =====================
+    const int i = warp >> 2;                        // query tile
+    const int q = warp & 3;                         // TMEM lane quarter
+    const int row = q0 + i * FA_BQ + q * 32 + lane; // query index within the utterance
+    const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16);
+    const uint32_t t_s = lane_base + FA_COL_S + uint32_t(i * FA_BK);
+    const uint32_t t_o = lane_base + FA_COL_O + uint32_t(i * FA_HD);
+    const uint32_t t_p = lane_base + FA_COL_P + uint32_t(i * 64);
+    const float kLog2e = 1.4426950408889634f;
+    float m_used = -INFINITY;      // stale running maximum (raw score units)
+    float l_run = 0.f;
+
+    for (int j = 0; j < n_blocks; ++j) {
+      mbar_wait(&s_full[i], uint32_t(j & 1));
+      tc_fence_after();
+      uint32_t r[FA_BK / 32][32];                    // this row's 128 raw scores (q was pre-scaled, CW:342)
+#pragma unroll
+      for (int c = 0; c < FA_BK / 32; ++c) tmem_ld_32x32b_x32(t_s + uint32_t(c * 32), r[c]);
+      tmem_ld_wait();
+      const int valid = p.kv_len - j * FA_BK;       // keys of this block that exist
+      if (valid < FA_BK) {
+#pragma unroll
+        for (int c = 0; c < FA_BK / 32; ++c)
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (c * 32 + e >= valid) r[c][e] = 0xff800000u;      // -inf
+      }
+      float mx = __uint_as_float(r[0][0]);
+#pragma unroll
+      for (int c = 0; c < FA_BK / 32; ++c)
+#pragma unroll
+        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(r[c][e]));
+      // P_i of the previous block has been consumed and O_i is stable once P V of block j-1 retired
+      if (j > 0) {
+        mbar_wait(&o_full[i], uint32_t((j - 1) & 1));
+        tc_fence_after();
+      }
+      const bool grow = mx > m_used + 5.545177f;     // 8 in log2 units; first block: m_used = -inf
+      if (__any_sync(0xffffffffu, grow)) {
+        const float m_new = grow ? mx : m_used;
+        const float alpha = (m_used == -INFINITY) ? 0.f : fast_exp2((m_used - m_new) * kLog2e);
+        l_run *= alpha;
+        m_used = m_new;
+        if (j > 0) {                                 // block 0 writes O with accumulate = 0
+#pragma unroll
+          for (int c = 0; c < FA_HD / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(t_o + uint32_t(c * 32), o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+            tmem_st_32x32b_x32(t_o + uint32_t(c * 32), o);
+          }
+        }
+      }
+      const float neg_m = -m_used * kLog2e;
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < FA_BK / 64; ++c) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int col = c * 64 + 2 * e;
+          const float p0 = fast_exp2(fmaf(__uint_as_float(r[col >> 5][col & 31]), kLog2e, neg_m));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(r[(col + 1) >> 5][(col + 1) & 31]), kLog2e, neg_m));
+          sum0 += p0;
+          sum1 += p1;
+          pk[e] = pack_bf16x2(p0, p1);
+        }
+        tmem_st_32x32b_x32(t_p + uint32_t(c * 32), pk);
+      }
+      const float sum = sum0 + sum1;
+      l_run += sum;
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[i]);
+    }
+
+    // ---- output: O_i / l ----
+    mbar_wait(&o_full[i], uint32_t((n_blocks - 1) & 1));
+    tc_fence_after();
+    const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+    __nv_bfloat16* orow = p.o + (int64_t(b) * p.q_len + row) * p.ldo + head * FA_HD;
+#pragma unroll
+    for (int c = 0; c < FA_HD / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(t_o + uint32_t(c * 32), r);
+      tmem_ld_wait();
+      if (row < p.q_len) {
+        uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(r[8 * e + 0]) * inv, __uint_as_float(r[8 * e + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(r[8 * e + 2]) * inv, __uint_as_float(r[8 * e + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(r[8 * e + 4]) * inv, __uint_as_float(r[8 * e + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(r[8 * e + 6]) * inv, __uint_as_float(r[8 * e + 7]) * inv);
+          dst[e] = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn fa_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// {64 * heads columns, rows, batch} view of a [batch * rows, ld] bf16 activation; box = 64 x 128 x 1
+static int make_map(EncodeTiledFn enc, CUtensorMap* m, const void* base, int heads, int rows, int batch, int ld) {
+  cuuint64_t dims[3] = {(cuuint64_t)heads * FA_HD, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)rows};
+  cuuint32_t box[3] = {FA_HD, FA_BQ, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error((int)r, "attention: tensor map encode failed (%d)", (int)r);
+  return 0;
+}
+
+bool attention_tcgen05_eligible(const AttnDesc& d) {
+  if (d.cu_q || d.cu_kv || d.causal) return false;
+  if (d.q_len < 2 * FA_BQ || d.kv_len < FA_BK) return false;           // small problems: the mma.sync kernel
+  if ((reinterpret_cast<uintptr_t>(d.q) | reinterpret_cast<uintptr_t>(d.k) | reinterpret_cast<uintptr_t>(d.v)) & 15)
+    return false;
+  if ((d.ldq | d.ldk | d.ldv | d.ldo) % 8 != 0) return false;
+  return true;
+}
+
+int launch_attention_tcgen05(const AttnDesc& d, cudaStream_t stream) {
+  EncodeTiledFn enc = fa_encode_fn();
+  if (!enc) return set_error(TASTE_E_NO_DEVICE, "cuTensorMapEncodeTiled entry point unavailable");
+  CUtensorMap mq, mk, mv;
+  int rc;
+  if ((rc = make_map(enc, &mq, d.q, d.heads, d.q_len, d.batch, d.ldq))) return rc;
+  if ((rc = make_map(enc, &mk, d.k, d.heads, d.kv_len, d.batch, d.ldk))) return rc;
+  if ((rc = make_map(enc, &mv, d.v, d.heads, d.kv_len, d.batch, d.ldv))) return rc;
+  static bool configured = false;
+  if (!configured) {
+    TASTE_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM));
+    configured = true;
+  }
+  FaParams p;
+  p.o = static_cast<__nv_bfloat16*>(d.o);
+  p.ldo = d.ldo;
+  p.q_len = d.q_len;
+  p.kv_len = d.kv_len;
+  dim3 grid((d.q_len + 2 * FA_BQ - 1) / (2 * FA_BQ), d.heads, d.batch);
+  const double pairs = double(d.batch) * d.q_len * d.kv_len;
+  ProfScope ps(stream, d.kclass == KC_ATTN_ENC ? KC_ATTN_ENC : KC_ATTN_TC, 4.0 * pairs * FA_HD * d.heads,
+               2.0 * FA_HD * d.heads * double(d.batch) * (2.0 * d.q_len + 2.0 * d.kv_len));
+  attention_tcgen05_kernel<<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
+  TASTE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace taste

@@ -79,7 +79,10 @@ struct AttnDesc {
   int total_q = 0;       // sum of query rows (accounting only; 0 = batch * q_len)
   int kclass = KC_ATTN_AGG;
 };
-int launch_attention(const AttnDesc& d, cudaStream_t stream);
+int launch_attention(const AttnDesc& d, cudaStream_t stream);      // dispatches between the two kernels below
+bool attention_tcgen05_eligible(const AttnDesc& d);
+int launch_attention_tcgen05(const AttnDesc& d, cudaStream_t stream);
+void set_attention_mode(int mode);                                  // 0 = automatic, 1 = always the mma.sync kernel
 
 // ---- elementwise (elementwise.cu) ----
 int launch_layernorm(const float* x, const float* w, const float* b, void* y, int rows, int d, bool out_bf16,

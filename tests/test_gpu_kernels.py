@@ -113,8 +113,14 @@ def _attn_ref(q, k, v, causal):
     return torch.softmax(s, -1) @ v.double()
 
 
-@pytest.mark.parametrize("B,S,H", [(1, 64, 1), (2, 1500, 3), (3, 200, 2), (2, 65, 2)])
-def test_attention_fixed(lib, B, S, H):
+@pytest.mark.parametrize("B,S,H", [(1, 64, 1), (2, 1500, 3), (3, 200, 2), (2, 65, 2), (1, 256, 1), (2, 300, 2),
+                                   (1, 1536, 2), (3, 1000, 4), (1, 257, 1)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_attention_fixed(lib, B, S, H, mode):
+    """mode 0: tcgen05/TMEM kernel when S >= 256 (encoder shape), mode 1: mma.sync kernel everywhere."""
+    if mode == 1 and S < 256:
+        pytest.skip("already the mma.sync kernel in mode 0")
+    assert lib.taste_attention_set_mode(mode) == 0
     torch.manual_seed(B * 100 + S)
     D = H * 64
     qkv = (torch.randn(B * S, 3 * D, device="cuda") * 0.7).bfloat16()
@@ -122,6 +128,8 @@ def test_attention_fixed(lib, B, S, H):
     q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
     _lib.check(lib.taste_attention_bf16(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(o), 3 * D, 3 * D, 3 * D, D,
                                         None, None, S, S, B, H, 0, _stream()), "attn")
+    torch.cuda.synchronize()
+    lib.taste_attention_set_mode(0)
     qh = q.float().view(B, S, H, 64).transpose(1, 2)
     kh = k.float().view(B, S, H, 64).transpose(1, 2)
     vh = v.float().view(B, S, H, 64).transpose(1, 2)
