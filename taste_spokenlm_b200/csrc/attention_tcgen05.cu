@@ -14,6 +14,8 @@
 //
 // Roles (320 threads): warps 0-3 softmax tile 0, warps 4-7 softmax tile 1 (warp w owns TMEM lanes 32*(w%4)..+31),
 // warp 8 TMA producer, warp 9 MMA issuer + TMEM allocator.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -33,11 +35,19 @@ constexpr uint32_t FA_COL_O = 256;    // O0 [256,320) O1 [320,384)
 constexpr uint32_t FA_COL_P = 384;    // P0 [384,448) P1 [448,512)   (bf16 pairs: 64 columns per 128 keys)
 
 struct FaParams {
+  long long* dbg;      // timeline trace (VAR 4 only)
   __nv_bfloat16* o;
   int ldo;
   int q_len, kv_len;
 };
 
+#define FA_TRACE(slot, idx)                                                                         \
+  do {                                                                                              \
+    if (VAR == 4 && p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0)   \
+      p.dbg[(slot) * 256 + (idx)] = clock64();                                                     \
+  } while (0)
+
+template <int VAR>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                          const __grid_constant__ CUtensorMap tma_v, const FaParams p) {
@@ -50,8 +60,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
   uint64_t* kv_full = bars + 1;                         // [FA_STAGES]
   uint64_t* kv_empty = kv_full + FA_STAGES;             // [FA_STAGES]
   uint64_t* s_full = kv_empty + FA_STAGES;              // [2]  S_i ready            (MMA -> softmax)
-  uint64_t* p_full = s_full + 2;                        // [2]  P_i written, S_i free (softmax -> MMA), 4 warp arrivals
-  uint64_t* o_full = p_full + 2;                        // [2]  P_i V done           (MMA -> softmax)
+  uint64_t* s_free = s_full + 2;                        // [2]  S_i copied to registers (softmax -> MMA), 4 warp arrivals
+  uint64_t* p_full = s_free + 2;                        // [2]  P_i written           (softmax -> MMA), 4 warp arrivals
+  uint64_t* o_full = p_full + 2;                        // [2]  P_i V done            (MMA -> softmax)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -72,6 +83,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 4);
       mbar_init(&p_full[i], 4);
       mbar_init(&o_full[i], 1);
     }
@@ -86,79 +98,101 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Producer and MMA warps run warp-uniform loops and elect one lane around the TMA / tcgen05 instructions (inside an
+  // `if (lane == 0)` region every UTCHMMA is wrapped in an ELECT loop: ~90 cycles per MMA, measured with FA_TRACE).
   if (warp == 8) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
+    // ===================== TMA producer =====================
+    if (elect_one()) {
       mbar_expect_tx(q_full, 2 * FA_TILE_BYTES);
       tma_load_3d(sQ, &tma_q, q_full, head * FA_HD, q0, b);
       tma_load_3d(sQ + FA_TILE_BYTES, &tma_q, q_full, head * FA_HD, q0 + FA_BQ, b);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < n_blocks; ++j) {
-        mbar_wait(&kv_empty[stage], phase ^ 1);
-        uint8_t* sk = sKV + size_t(2 * stage) * FA_TILE_BYTES;
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < n_blocks; ++j) {
+      mbar_wait_relaxed(&kv_empty[stage], phase ^ 1);
+      uint8_t* sk = sKV + size_t(2 * stage) * FA_TILE_BYTES;
+      if (elect_one()) {
         mbar_expect_tx(&kv_full[stage], 2 * FA_TILE_BYTES);
         tma_load_3d(sk, &tma_k, &kv_full[stage], head * FA_HD, j * FA_BK, b);
         tma_load_3d(sk + FA_TILE_BYTES, &tma_v, &kv_full[stage], head * FA_HD, j * FA_BK, b);
-        if (++stage == FA_STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
+      }
+      __syncwarp();
+      if (++stage == FA_STAGES) {
+        stage = 0;
+        phase ^= 1;
       }
     }
-    __syncwarp();
   } else if (warp == 9) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc_qk = umma_idesc(FA_BQ, FA_BK, 1, 0, 0);        // A, B K-major
-      constexpr uint32_t idesc_pv = umma_idesc(FA_BQ, FA_HD, 1, 0, 1);        // A from TMEM, B (V) MN-major
-      auto issue_qk = [&](int i, int stage) {
-        const uint64_t da = umma_desc_k_sw128(smem_u32(sQ + size_t(i) * FA_TILE_BYTES));
-        const uint64_t db = umma_desc_k_sw128(smem_u32(sKV + size_t(2 * stage) * FA_TILE_BYTES));
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_qk = umma_idesc(FA_BQ, FA_BK, 1, 0, 0);        // A, B K-major
+    constexpr uint32_t idesc_pv = umma_idesc(FA_BQ, FA_HD, 1, 0, 1);        // A from TMEM, B (V) MN-major
+    auto issue_qk = [&](int i, int stage) {
+      const uint64_t da = umma_desc_k_sw128(smem_u32(sQ + size_t(i) * FA_TILE_BYTES));
+      const uint64_t db = umma_desc_k_sw128(smem_u32(sKV + size_t(2 * stage) * FA_TILE_BYTES));
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < FA_HD / 16; ++k)
           umma_ss(tmem_base + FA_COL_S + uint32_t(i * FA_BK), da + uint64_t(k * 2), db + uint64_t(k * 2), idesc_qk,
                   k != 0 ? 1u : 0u);
         umma_commit(&s_full[i]);
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      issue_qk(0, 0);
-      issue_qk(1, 0);
-      int stage = 0;
-      uint32_t phase = 0;          // phase of kv_full[stage] for block j
-      for (int j = 0; j < n_blocks; ++j) {
-        int nstage = stage + 1;
-        uint32_t nphase = phase;
-        if (nstage == FA_STAGES) {
-          nstage = 0;
-          nphase ^= 1;
-        }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          mbar_wait(&p_full[i], uint32_t(j & 1));
-          tc_fence_after();
-          if (j + 1 < n_blocks) {
-            if (i == 0) {
-              mbar_wait(&kv_full[nstage], nphase);
-              tc_fence_after();
-            }
-            issue_qk(i, nstage);                 // next block's scores first: the softmax warps wait on these
-          }
-          const uint64_t dv = umma_desc_mn_sw128(smem_u32(sKV + size_t(2 * stage + 1) * FA_TILE_BYTES), 0);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    issue_qk(0, 0);
+    int stage = 0;
+    uint32_t phase = 0;          // phase of kv_full[stage] for block j
+    for (int j = 0; j < n_blocks; ++j) {
+      int nstage = stage + 1;
+      uint32_t nphase = phase;
+      if (nstage == FA_STAGES) {
+        nstage = 0;
+        nphase ^= 1;
+      }
+      const bool more = j + 1 < n_blocks;
+      const uint64_t dv = umma_desc_mn_sw128(smem_u32(sKV + size_t(2 * stage + 1) * FA_TILE_BYTES), 0);
+      auto issue_pv = [&](int i, bool release_kv) {
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < FA_BK / 16; ++k)     // 16 keys per MMA: 8 TMEM columns of P, 2048 B of V
             umma_ts(tmem_base + FA_COL_O + uint32_t(i * FA_HD), tmem_base + FA_COL_P + uint32_t(i * 64 + k * 8),
                     dv + uint64_t(k * (2048 >> 4)), idesc_pv, (j | k) != 0 ? 1u : 0u);
           umma_commit(&o_full[i]);
-          if (i == 1) umma_commit(&kv_empty[stage]);
+          if (release_kv) umma_commit(&kv_empty[stage]);
         }
-        stage = nstage;
-        phase = nphase;
-      }
+        __syncwarp();
+      };
+      // The two warpgroups run half a block apart (tile 1 starts when tile 0 is half way through its first
+      // block), so one is in its exp2-heavy pass while the other reads / reduces its scores.  The waits below
+      // follow that order of events: S0 copied, P0 written, S1 copied, P1 written.
+      if (more) mbar_wait(&kv_full[nstage], nphase);
+      mbar_wait(&s_free[0], uint32_t(j & 1));
+      FA_TRACE(2, j * 8 + 0);
+      tc_fence_after();
+      if (more) issue_qk(0, nstage);
+      if (j == 0) issue_qk(1, 0);
+      FA_TRACE(2, j * 8 + 1);
+      mbar_wait(&p_full[0], uint32_t(j & 1));
+      FA_TRACE(2, j * 8 + 2);
+      tc_fence_after();
+      issue_pv(0, false);
+      FA_TRACE(2, j * 8 + 3);
+      mbar_wait(&s_free[1], uint32_t(j & 1));
+      FA_TRACE(2, j * 8 + 4);
+      tc_fence_after();
+      if (more) issue_qk(1, nstage);
+      mbar_wait(&p_full[1], uint32_t(j & 1));
+      FA_TRACE(2, j * 8 + 5);
+      tc_fence_after();
+      issue_pv(1, true);
+      FA_TRACE(2, j * 8 + 6);
+      stage = nstage;
+      phase = nphase;
     }
-    __syncwarp();
   } else {
     // ===================== softmax + output (warps 0-7) =====================
     const int i = warp >> 2;                        // query tile
@@ -173,63 +207,88 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
     float l_run = 0.f;
 
     for (int j = 0; j < n_blocks; ++j) {
+      FA_TRACE(i, j * 8 + 0);
       mbar_wait(&s_full[i], uint32_t(j & 1));
+      FA_TRACE(i, j * 8 + 1);
       tc_fence_after();
-      uint32_t r[FA_BK / 32][32];                    // this row's 128 raw scores (q was pre-scaled, CW:342)
-#pragma unroll
-      for (int c = 0; c < FA_BK / 32; ++c) tmem_ld_32x32b_x32(t_s + uint32_t(c * 32), r[c]);
-      tmem_ld_wait();
+      // The S tile is read twice from TMEM in 32-column chunks (pass 1: row maximum, pass 2: exponentials), always
+      // with the NEXT chunk's tcgen05.ld in flight while the current one is processed, so only the first load of a
+      // block exposes the TMEM latency.  Live registers: two chunks (64 scores) + 32 packed probabilities.
       const int valid = p.kv_len - j * FA_BK;       // keys of this block that exist
-      if (valid < FA_BK) {
+      uint32_t r[2][32];
+      float mx = -INFINITY;
+      tmem_ld_32x32b_x32(t_s, r[0]);
 #pragma unroll
-        for (int c = 0; c < FA_BK / 32; ++c)
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld_wait();
+        tmem_ld_32x32b_x32(t_s + uint32_t(((c + 1) & 3) * 32), r[(c + 1) & 1]);   // c == 3: chunk 0 again, for pass 2
+        if (valid < FA_BK) {
 #pragma unroll
           for (int e = 0; e < 32; ++e)
-            if (c * 32 + e >= valid) r[c][e] = 0xff800000u;      // -inf
-      }
-      float mx = __uint_as_float(r[0][0]);
+            if (c * 32 + e >= valid) r[c & 1][e] = 0xff800000u;      // -inf
+        }
 #pragma unroll
-      for (int c = 0; c < FA_BK / 32; ++c)
-#pragma unroll
-        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(r[c][e]));
-      // P_i of the previous block has been consumed and O_i is stable once P V of block j-1 retired
-      if (j > 0) {
-        mbar_wait(&o_full[i], uint32_t((j - 1) & 1));
-        tc_fence_after();
+        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(r[c & 1][e]));
       }
+      FA_TRACE(i, j * 8 + 2);
       const bool grow = mx > m_used + 5.545177f;     // 8 in log2 units; first block: m_used = -inf
-      if (__any_sync(0xffffffffu, grow)) {
+      const bool any_grow = __any_sync(0xffffffffu, grow);
+      float alpha = 1.0f;
+      if (any_grow) {
         const float m_new = grow ? mx : m_used;
-        const float alpha = (m_used == -INFINITY) ? 0.f : fast_exp2((m_used - m_new) * kLog2e);
+        alpha = (m_used == -INFINITY) ? 0.f : fast_exp2((m_used - m_new) * kLog2e);
         l_run *= alpha;
         m_used = m_new;
-        if (j > 0) {                                 // block 0 writes O with accumulate = 0
-#pragma unroll
-          for (int c = 0; c < FA_HD / 32; ++c) {
-            uint32_t o[32];
-            tmem_ld_32x32b_x32(t_o + uint32_t(c * 32), o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-            tmem_st_32x32b_x32(t_o + uint32_t(c * 32), o);
-          }
-        }
       }
+      // pass 2: p = exp2(s * log2e - m * log2e), row sum, bf16 P back to TMEM
       const float neg_m = -m_used * kLog2e;
       float sum0 = 0.f, sum1 = 0.f;
+      uint32_t pk[32];
 #pragma unroll
-      for (int c = 0; c < FA_BK / 64; ++c) {
-        uint32_t pk[32];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int col = c * 64 + 2 * e;
-          const float p0 = fast_exp2(fmaf(__uint_as_float(r[col >> 5][col & 31]), kLog2e, neg_m));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(r[(col + 1) >> 5][(col + 1) & 31]), kLog2e, neg_m));
-          sum0 += p0;
-          sum1 += p1;
-          pk[e] = pack_bf16x2(p0, p1);
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld_wait();
+        if (c < 3) {
+          tmem_ld_32x32b_x32(t_s + uint32_t((c + 1) * 32), r[(c + 1) & 1]);
+        } else {                                     // every read of S has landed: the next block's QK^T may overwrite it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free[i]);
+          FA_TRACE(i, j * 8 + 3);
         }
-        tmem_st_32x32b_x32(t_p + uint32_t(c * 32), pk);
+        if (valid < FA_BK) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (c * 32 + e >= valid) r[c & 1][e] = 0xff800000u;
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          float p0 = fmaf(__uint_as_float(r[c & 1][2 * e]), kLog2e, neg_m);
+          float p1 = fmaf(__uint_as_float(r[c & 1][2 * e + 1]), kLog2e, neg_m);
+          if (VAR != 1) { p0 = fast_exp2(p0); p1 = fast_exp2(p1); }
+          if (VAR != 3) { sum0 += p0; sum1 += p1; }
+          pk[(c & 1) * 16 + e] = (VAR == 2) ? (__float_as_uint(p0) ^ __float_as_uint(p1)) : pack_bf16x2(p0, p1);
+        }
+        if (c == 1 && j > 0) {
+          // Only now is the previous block's P V needed: P_i has been consumed (it may be overwritten) and O_i is
+          // stable (it may be rescaled).
+ FA_TRACE(i, j * 8 + 4);
+          mbar_wait(&o_full[i], uint32_t((j - 1) & 1));
+          FA_TRACE(i, j * 8 + 5);
+          tc_fence_after();
+          if (any_grow) {
+            tmem_ld_wait();                          // drain the in-flight S chunk before reusing the wait below
+#pragma unroll
+            for (int cc = 0; cc < FA_HD / 32; ++cc) {
+              uint32_t o[32];
+              tmem_ld_32x32b_x32(t_o + uint32_t(cc * 32), o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+              tmem_st_32x32b_x32(t_o + uint32_t(cc * 32), o);
+            }
+          }
+        }
+        if (c & 1) tmem_st_32x32b_x32(t_p + uint32_t((c >> 1) * 32), pk);
       }
       const float sum = sum0 + sum1;
       l_run += sum;
@@ -237,6 +296,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[i]);
+      FA_TRACE(i, j * 8 + 6);
     }
 
     // ---- output: O_i / l ----
@@ -301,6 +361,9 @@ static int make_map(EncodeTiledFn enc, CUtensorMap* m, const void* base, int hea
   return 0;
 }
 
+static long long* g_fa_trace = nullptr;
+extern "C" void taste_dbg_attention_trace(void* dev_buf) { g_fa_trace = static_cast<long long*>(dev_buf); }
+
 bool attention_tcgen05_eligible(const AttnDesc& d) {
   if (d.cu_q || d.cu_kv || d.causal) return false;
   if (d.q_len < 2 * FA_BQ || d.kv_len < FA_BK) return false;           // small problems: the mma.sync kernel
@@ -320,10 +383,17 @@ int launch_attention_tcgen05(const AttnDesc& d, cudaStream_t stream) {
   if ((rc = make_map(enc, &mv, d.v, d.heads, d.kv_len, d.batch, d.ldv))) return rc;
   static bool configured = false;
   if (!configured) {
-    TASTE_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM));
+    TASTE_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM));
+    TASTE_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM));
+    TASTE_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM));
+    TASTE_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM));
+    TASTE_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM));
     configured = true;
   }
+  const char* ev = getenv("TASTE_FA_VAR");
+  const int var = ev ? atoi(ev) : 0;
   FaParams p;
+  p.dbg = g_fa_trace;
   p.o = static_cast<__nv_bfloat16*>(d.o);
   p.ldo = d.ldo;
   p.q_len = d.q_len;
@@ -332,7 +402,11 @@ int launch_attention_tcgen05(const AttnDesc& d, cudaStream_t stream) {
   const double pairs = double(d.batch) * d.q_len * d.kv_len;
   ProfScope ps(stream, d.kclass == KC_ATTN_ENC ? KC_ATTN_ENC : KC_ATTN_TC, 4.0 * pairs * FA_HD * d.heads,
                2.0 * FA_HD * d.heads * double(d.batch) * (2.0 * d.q_len + 2.0 * d.kv_len));
-  attention_tcgen05_kernel<<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
+  if (var == 1) attention_tcgen05_kernel<1><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
+  else if (var == 2) attention_tcgen05_kernel<2><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
+  else if (var == 4) attention_tcgen05_kernel<4><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
+  else if (var == 3) attention_tcgen05_kernel<3><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
+  else attention_tcgen05_kernel<0><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
   TASTE_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -49,11 +49,41 @@ TASTE_DEVINL uint64_t global_timer_ns() {
 }
 TASTE_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = global_timer_ns();
+  uint64_t t0 = 0;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3FFu) == 0 && global_timer_ns() - t0 > TASTE_WAIT_LIMIT_NS) __trap();
+    if ((++spins & 0xFFFFu) == 0) {               // rare: keep the spin body to a handful of instructions
+      const uint64_t t = global_timer_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > TASTE_WAIT_LIMIT_NS) __trap();
+    }
   }
+}
+// Same, for roles with slack (TMA producers): backs off between polls so the spin does not take issue slots from
+// the compute warps that share the scheduler.
+TASTE_DEVINL void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint64_t t0 = 0;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if ((++spins & 0xFFFu) == 0) {
+      const uint64_t t = global_timer_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > TASTE_WAIT_LIMIT_NS) __trap();
+    }
+  }
+}
+// One lane of a fully converged warp (warp-uniform control flow around it lets the compiler emit tcgen05 / TMA
+// instructions once, instead of a per-active-lane ELECT loop as inside an `if (lane == 0)` region).
+TASTE_DEVINL bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 TASTE_DEVINL void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 TASTE_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -144,72 +144,75 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   const uint32_t tmem_base = *tmem_slot;
   const int kb_total = p.taps * p.kb_per_tap;
 
+  // Producer and MMA warps run their loops with all 32 lanes (warp-uniform control flow) and elect one lane around
+  // the TMA / tcgen05 instructions: inside an `if (lane == 0)` region the compiler wraps every UTCHMMA / UTMALDG in
+  // an ELECT loop (~90 cycles per MMA measured), which made the issuing thread the bottleneck.
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles;
-        const int mg = tile / p.n_tiles;
-        const int b = mg / p.m_tiles_per_batch;
-        const int mt = mg - b * p.m_tiles_per_batch;
-        for (int kb = 0; kb < kb_total; ++kb) {
-          const int tap = kb / p.kb_per_tap;
-          const int kc = kb - tap * p.kb_per_tap;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + size_t(stage) * Cfg::kStageBytes;
-          uint8_t* sb = sa + Cfg::kABytes;
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles;
+      const int mg = tile / p.n_tiles;
+      const int b = mg / p.m_tiles_per_batch;
+      const int mt = mg - b * p.m_tiles_per_batch;
+      for (int kb = 0; kb < kb_total; ++kb) {
+        const int tap = kb / p.kb_per_tap;
+        const int kc = kb - tap * p.kb_per_tap;
+        mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + size_t(stage) * Cfg::kStageBytes;
+        uint8_t* sb = sa + Cfg::kABytes;
+        const int ts = tap == 0 ? p.tap_s[0] : (tap == 1 ? p.tap_s[1] : p.tap_s[2]);
+        const int tr = tap == 0 ? p.tap_dr[0] : (tap == 1 ? p.tap_dr[1] : p.tap_dr[2]);
+        if (elect_one()) {
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          const int ts = tap == 0 ? p.tap_s[0] : (tap == 1 ? p.tap_s[1] : p.tap_s[2]);
-          const int tr = tap == 0 ? p.tap_dr[0] : (tap == 1 ? p.tap_dr[1] : p.tap_dr[2]);
           tma_load_4d(sa, &tma_a, &full_bar[stage], kc * BK, ts, mt * BM + tr, b);
           tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, nt * BN);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc = umma_idesc(BM, BN, /*bf16*/ 1, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[as], aphase ^ 1);
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc(BM, BN, /*bf16*/ 1, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + uint32_t(as * BN);
+      for (int kb = 0; kb < kb_total; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + uint32_t(as * BN);
-        for (int kb = 0; kb < kb_total; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + size_t(stage) * Cfg::kStageBytes);
-          const uint64_t da = umma_desc_k_sw128(sa);
-          const uint64_t db = umma_desc_k_sw128(sa + Cfg::kABytes);
+        const uint32_t sa = smem_u32(smem + size_t(stage) * Cfg::kStageBytes);
+        const uint64_t da = umma_desc_k_sw128(sa);
+        const uint64_t db = umma_desc_k_sw128(sa + Cfg::kABytes);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128-B swizzle row: +2 in the (addr >> 4) field
             umma_ss(d_tmem, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);      // frees the smem slot when these MMAs retire
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+          if (kb == kb_total - 1) umma_commit(&tfull_bar[as]);   // accumulator complete
         }
-        umma_commit(&tfull_bar[as]);           // accumulator complete
-        if (++as == 2) {
-          as = 0;
-          aphase ^= 1;
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
     }
-    __syncwarp();
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
@@ -311,41 +314,41 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const _
   const int kb_total = p.taps * p.kb_per_tap;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer (both CTAs) =====================
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = pair; tile < p.total_tiles; tile += n_pairs) {
-        const int nt = tile % p.n_tiles;
-        const int mg = tile / p.n_tiles;
-        const int b = mg / p.m_tiles_per_batch;
-        const int mt = mg - b * p.m_tiles_per_batch;
-        const int row0 = mt * (2 * BM) + int(rank) * BM;
-        const int col0 = nt * BN2 + int(rank) * (BN2 / 2);
-        for (int kb = 0; kb < kb_total; ++kb) {
-          const int tap = kb / p.kb_per_tap;
-          const int kc = kb - tap * p.kb_per_tap;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + size_t(stage) * Cfg::kStageBytes;
-          uint8_t* sb = sa + Cfg::kABytes;
-          // Both CTAs' TMA bytes are counted on the LEADER's barrier; only the leader arrives (expecting both halves).
-          // The peer cannot run a phase ahead: its slot is released by the same multicast commit as the leader's.
-          const uint32_t lead_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
+    // ===================== TMA producer (both CTAs; warp-uniform loop, one elected lane issues) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair; tile < p.total_tiles; tile += n_pairs) {
+      const int nt = tile % p.n_tiles;
+      const int mg = tile / p.n_tiles;
+      const int b = mg / p.m_tiles_per_batch;
+      const int mt = mg - b * p.m_tiles_per_batch;
+      const int row0 = mt * (2 * BM) + int(rank) * BM;
+      const int col0 = nt * BN2 + int(rank) * (BN2 / 2);
+      for (int kb = 0; kb < kb_total; ++kb) {
+        const int tap = kb / p.kb_per_tap;
+        const int kc = kb - tap * p.kb_per_tap;
+        mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + size_t(stage) * Cfg::kStageBytes;
+        uint8_t* sb = sa + Cfg::kABytes;
+        // Both CTAs' TMA bytes are counted on the LEADER's barrier; only the leader arrives (expecting both halves).
+        // The peer cannot run a phase ahead: its slot is released by the same multicast commit as the leader's.
+        const uint32_t lead_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
+        const int ts = tap == 0 ? p.tap_s[0] : (tap == 1 ? p.tap_s[1] : p.tap_s[2]);
+        const int tr = tap == 0 ? p.tap_dr[0] : (tap == 1 ? p.tap_dr[1] : p.tap_dr[2]);
+        if (elect_one()) {
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-          const int ts = tap == 0 ? p.tap_s[0] : (tap == 1 ? p.tap_s[1] : p.tap_s[2]);
-          const int tr = tap == 0 ? p.tap_dr[0] : (tap == 1 ? p.tap_dr[1] : p.tap_dr[2]);
           tma_load_4d_2sm(sa, &tma_a, lead_full, kc * BK, ts, row0 + tr, b);
           tma_load_2d_2sm(sb, &tma_b, lead_full, kb * BK, col0);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    if (leader) {
       // ===================== MMA issuer (leader CTA only) =====================
       constexpr uint32_t idesc = umma_idesc(2 * BM, BN2, /*bf16*/ 1, 0, 0);
       int stage = 0;
@@ -362,23 +365,25 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const _
           const uint32_t sa = smem_u32(smem + size_t(stage) * Cfg::kStageBytes);
           const uint64_t da = umma_desc_k_sw128(sa);
           const uint64_t db = umma_desc_k_sw128(sa + Cfg::kABytes);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_ss_2sm(d_tmem, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_2sm(&empty_bar[stage], 0x3);    // both CTAs may refill this slot once the MMAs retire
+            for (int k = 0; k < BK / 16; ++k)
+              umma_ss_2sm(d_tmem, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2sm(&empty_bar[stage], 0x3);    // both CTAs may refill this slot once the MMAs retire
+            if (kb == kb_total - 1) umma_commit_2sm(&tfull_bar[as], 0x3);
+          }
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_2sm(&tfull_bar[as], 0x3);
         if (++as == 2) {
           as = 0;
           aphase ^= 1;
         }
       }
     }
-    __syncwarp();
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs) =====================
     const int q = warp & 3;
