@@ -26,6 +26,9 @@ constexpr int FA_BK = 128;          // keys per block
 constexpr int FA_HD = 64;
 constexpr int FA_STAGES = 4;
 constexpr int FA_THREADS = 320;
+#ifndef FA_POLY
+#define FA_POLY 7                   // of every 16 score pairs, this many take the polynomial exp2 path
+#endif
 constexpr uint32_t FA_TILE_BYTES = FA_BQ * FA_HD * 2;      // 16 KB: one Q, K or V tile
 constexpr size_t FA_SMEM = 1024 + size_t(2 + 2 * FA_STAGES) * FA_TILE_BYTES + 256;
 
@@ -242,7 +245,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
       }
       // pass 2: p = exp2(s * log2e - m * log2e), row sum, bf16 P back to TMEM
       const float neg_m = -m_used * kLog2e;
-      float sum0 = 0.f, sum1 = 0.f;
+      const uint64_t negm2 = f2_pack(neg_m, neg_m);
+      const uint64_t log2e2 = f2_pack(kLog2e, kLog2e);
+      uint64_t sum2 = f2_pack(0.f, 0.f);
       uint32_t pk[32];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -260,13 +265,22 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
           for (int e = 0; e < 32; ++e)
             if (c * 32 + e >= valid) r[c & 1][e] = 0xff800000u;
         }
+        // Exponentials in pairs (packed FFMA2 / FADD2).  16/clk/SM of MUFU.EX2 would cap the tensor pipe at 50 %, so
+        // FA_POLY of every 16 pairs are evaluated on the FMA pipe instead (exp2_poly2).
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          float p0 = fmaf(__uint_as_float(r[c & 1][2 * e]), kLog2e, neg_m);
-          float p1 = fmaf(__uint_as_float(r[c & 1][2 * e + 1]), kLog2e, neg_m);
-          if (VAR != 1) { p0 = fast_exp2(p0); p1 = fast_exp2(p1); }
-          if (VAR != 3) { sum0 += p0; sum1 += p1; }
-          pk[(c & 1) * 16 + e] = (VAR == 2) ? (__float_as_uint(p0) ^ __float_as_uint(p1)) : pack_bf16x2(p0, p1);
+          const uint64_t t2 = f2_fma(f2_pack(__uint_as_float(r[c & 1][2 * e]), __uint_as_float(r[c & 1][2 * e + 1])),
+                                     log2e2, negm2);
+          float p0, p1;
+          if (((e * FA_POLY) & 15) < FA_POLY && FA_POLY > 0) {       // evenly spread FA_POLY of 16
+            exp2_poly2(t2, p0, p1);
+          } else {
+            f2_unpack(t2, p0, p1);
+            p0 = fast_exp2(p0);
+            p1 = fast_exp2(p1);
+          }
+          sum2 = f2_add(sum2, f2_pack(p0, p1));
+          pk[(c & 1) * 16 + e] = pack_bf16x2(p0, p1);
         }
         if (c == 1 && j > 0) {
           // Only now is the previous block's P V needed: P_i has been consumed (it may be overwritten) and O_i is
@@ -290,6 +304,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
         }
         if (c & 1) tmem_st_32x32b_x32(t_p + uint32_t((c >> 1) * 32), pk);
       }
+      float sum0, sum1;
+      f2_unpack(sum2, sum0, sum1);
       const float sum = sum0 + sum1;
       l_run += sum;
       tmem_st_wait();
@@ -384,9 +400,6 @@ int launch_attention_tcgen05(const AttnDesc& d, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     TASTE_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM));
-    TASTE_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM));
-    TASTE_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM));
-    TASTE_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM));
     TASTE_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM));
     configured = true;
   }
@@ -402,10 +415,7 @@ int launch_attention_tcgen05(const AttnDesc& d, cudaStream_t stream) {
   const double pairs = double(d.batch) * d.q_len * d.kv_len;
   ProfScope ps(stream, d.kclass == KC_ATTN_ENC ? KC_ATTN_ENC : KC_ATTN_TC, 4.0 * pairs * FA_HD * d.heads,
                2.0 * FA_HD * d.heads * double(d.batch) * (2.0 * d.q_len + 2.0 * d.kv_len));
-  if (var == 1) attention_tcgen05_kernel<1><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
-  else if (var == 2) attention_tcgen05_kernel<2><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
-  else if (var == 4) attention_tcgen05_kernel<4><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
-  else if (var == 3) attention_tcgen05_kernel<3><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
+  if (var == 4) attention_tcgen05_kernel<4><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
   else attention_tcgen05_kernel<0><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
   TASTE_CUDA_OK(cudaGetLastError());
   return 0;

@@ -318,6 +318,47 @@ TASTE_DEVINL float fast_exp2(float x) {
   return y;
 }
 
+// ---- packed fp32 x 2 arithmetic (FFMA2 / FADD2 on sm_100): halves the FMA-pipe issue slots of elementwise code ----
+TASTE_DEVINL uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+TASTE_DEVINL void f2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+TASTE_DEVINL uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+TASTE_DEVINL uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// 2^t for two values on the FMA pipe (no MUFU): t = n + f, n = round(t) via the 1.5 * 2^23 magic add, 2^f by a
+// degree-3 minimax polynomial on [-0.5, 0.5] (max relative error 7.5e-5, far below bf16 resolution), 2^n by adding n
+// to the exponent field.  t is clamped at -126 (results below 2^-126 flush towards 1.2e-38, harmless for softmax).
+TASTE_DEVINL void exp2_poly2(uint64_t t2, float& p0, float& p1) {
+  float t0, t1;
+  f2_unpack(t2, t0, t1);
+  t0 = fmaxf(t0, -126.0f);
+  t1 = fmaxf(t1, -126.0f);
+  const uint64_t t = f2_pack(t0, t1);
+  const uint64_t magic = f2_pack(12582912.0f, 12582912.0f);
+  const uint64_t nmagic = f2_pack(-12582912.0f, -12582912.0f);
+  const uint64_t u = f2_add(t, magic);                        // low mantissa bits = round(t)
+  const uint64_t n = f2_add(u, nmagic);
+  const uint64_t f = f2_fma(n, f2_pack(-1.0f, -1.0f), t);     // t - n  in [-0.5, 0.5]
+  uint64_t p = f2_fma(f, f2_pack(5.517166712e-02f, 5.517166712e-02f), f2_pack(2.426111220e-01f, 2.426111220e-01f));
+  p = f2_fma(p, f, f2_pack(6.932609858e-01f, 6.932609858e-01f));
+  p = f2_fma(p, f, f2_pack(9.999280736e-01f, 9.999280736e-01f));
+  float q0, q1, u0, u1;
+  f2_unpack(p, q0, q1);
+  f2_unpack(u, u0, u1);
+  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(u0) << 23));
+  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(u1) << 23));
+}
+
 TASTE_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -296,7 +296,8 @@ class TowerEngine(FrontendEngine):
         return tokens
 
     # ---- aggregator + pooling + RVQ on device-resident encoder states -------------------------------------------
-    def segment_and_quantize(self, h_last, h_t, ids_dev, wid_dev, lengths_host: np.ndarray, skip_vq: bool = False):
+    def segment_and_quantize(self, h_last, h_t, ids_dev, wid_dev, lengths_host: np.ndarray, skip_vq: bool = False,
+                             want_quantized: bool = True):
         """MT:144-185 after the encoder: token assembly, aggregator, prefix skip + word pooling + EOS drop, RVQ.
         `lengths_host` is the host copy of asr_token_lengths (the only host-side quantity the launch geometry needs)."""
         dev = self.device
@@ -318,7 +319,7 @@ class TowerEngine(FrontendEngine):
         if Tm != Tmax:
             raise ValueError(f"padded width {Tmax} != longest transcript {Tm}: the reference's mask/feature shapes "
                              f"disagree in this case (MT:181-184)")
-        return self.rvq_encode(z, lens32)
+        return self.rvq_encode(z, lens32, want_quantized=want_quantized)
 
     # ---- waveform -> indices with everything resident on the device (corpus driver path) ------------------------
     def tokenize_device(self, wav, n_samples, ids_dev, wid_dev, lengths_host, want_quantized: bool = True):
@@ -326,7 +327,7 @@ class TowerEngine(FrontendEngine):
         Returns (quantized [B,Tmax,D] fp32, indices [B,Tmax,Q] int64).  WF:87-113 -> MT:108-211."""
         _, feats = self.logmel(wav, n_samples, want_f32=False, want_bf16=True)
         h_last, h_t = self.encode(feats)
-        return self.segment_and_quantize(h_last, h_t, ids_dev, wid_dev, lengths_host)
+        return self.segment_and_quantize(h_last, h_t, ids_dev, wid_dev, lengths_host, want_quantized=want_quantized)
 
     # ---- the whole tower: MT:108-211 --------------------------------------------------------------------------
     def tower_forward(self, asr_token_ids, asr_token_lengths, audio_features, asr_word_ids, skip_vq: bool = False,

@@ -1,0 +1,91 @@
+"""Multi-GPU host logic on CPU: utterance sharding and the all-gather of counts + packed indices, world_size 2, gloo."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from taste_spokenlm_b200 import shard
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _token_counts(n=203, seed=4):
+    rng = np.random.default_rng(seed)
+    dur = rng.uniform(1, 30, n)
+    return np.clip(np.round(2.7 * dur + rng.normal(0, 2, n)), 1, 443).astype(int).tolist()
+
+
+def test_shards_partition_the_corpus_and_balance_lengths():
+    tc = _token_counts()
+    for world in (1, 2, 4, 8):
+        parts = [shard.shard_indices(tc, world, r) for r in range(world)]
+        allidx = np.concatenate(parts)
+        assert sorted(allidx.tolist()) == list(range(len(tc)))                      # disjoint and complete
+        sizes = [len(p) for p in parts]
+        assert max(sizes) - min(sizes) <= 1
+        loads = [sum(tc[i] for i in p) for p in parts]                              # same transcript-length mix
+        assert max(loads) - min(loads) <= 0.1 * np.mean(loads) + 64
+    owned = shard.shard_indices(tc, 2, 1)
+    seen = []
+    for b in shard.batches(owned, tc, 16):
+        assert 1 <= len(b) <= 16
+        lens = [tc[i] for i in b]
+        assert max(lens) // 16 - min(lens) // 16 <= 1                               # tight padding
+        seen += b.tolist()
+    assert seen == owned.tolist()
+    with pytest.raises(ValueError):
+        shard.shard_indices(tc, 2, 2)
+
+
+def _fake_indices(u, t):
+    g = torch.Generator().manual_seed(u)
+    return torch.randint(0, 512, (t, 4), generator=g, dtype=torch.int64)
+
+
+def _worker(rank, world, port, tc, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        owned = shard.shard_indices(tc, world, rank)
+        ids, res = [], []
+        for b in shard.batches(owned, tc, 8):
+            for u in b:
+                ids.append(int(u))
+                res.append(_fake_indices(int(u), tc[u]))
+        hdr, flat = shard.pack_results(ids, res)
+        got = shard.gather_indices(hdr, flat, 4)
+        assert [u for u, _ in got] == list(range(len(tc)))
+        for u, t in got:
+            assert t.dtype == torch.int16 and t.shape == (tc[u], 4)
+            assert torch.equal(t.to(torch.int64), _fake_indices(u, tc[u]))
+        torch.save(len(got), os.path.join(out_dir, f"ok{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_indices_world2_gloo(tmp_path):
+    tc = _token_counts(61, seed=9)
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, tc, str(tmp_path)), nprocs=2, join=True)
+    assert torch.load(tmp_path / "ok0.pt") == 61 and torch.load(tmp_path / "ok1.pt") == 61
+
+
+def test_gather_indices_single_process():
+    tc = [3, 1, 7]
+    hdr, flat = shard.pack_results([2, 0, 1], [_fake_indices(2, 7), _fake_indices(0, 3), _fake_indices(1, 1)])
+    got = shard.gather_indices(hdr, flat, 4)
+    assert [u for u, _ in got] == [0, 1, 2]
+    assert torch.equal(got[2][1].to(torch.int64), _fake_indices(2, 7))
+    hdr0, flat0 = shard.pack_results([], [])
+    assert shard.gather_indices(hdr0, flat0, 4) == []
