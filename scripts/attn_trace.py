@@ -9,16 +9,17 @@ st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 qkv = (torch.randn(B * S, 3 * D, device="cuda") * 0.7).bfloat16()
 o = torch.zeros(B * S, D, device="cuda", dtype=torch.bfloat16)
 q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
-dbg = torch.zeros(3 * 256, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(4 * 256, dtype=torch.int64, device="cuda")
 lib.taste_dbg_attention_trace(C.c_void_p(dbg.data_ptr()))
 for _ in range(3):
     _lib.check(lib.taste_attention_bf16(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(o), 3 * D, 3 * D, 3 * D, D, None, None, S, S, B, H, 0, st), "attn")
 torch.cuda.synchronize()
-t = dbg.cpu().view(3, 32, 8)
+t = dbg.cpu().view(4, 32, 8)
 t0 = int(t[0, 0, 0])
 names_wg = ["enter", "s_full", "pass1done", "s_free", "pre_o_wait", "o_full", "p_full_arrive"]
-names_mma = ["s_free0", "qk0_issued", "p_full0", "pv0_issued", "s_free1", "p_full1", "pv1_issued"]
+names_mma = ["s_free", "qk_issued", "p_full", "pv_issued"]
 for j in range(12):
     print(f"blk {j:2d} WG0:", " ".join(f"{n}={int(t[0,j,e])-t0}" for e, n in enumerate(names_wg)))
     print(f"       WG1:", " ".join(f"{n}={int(t[1,j,e])-t0}" for e, n in enumerate(names_wg)))
-    print(f"       MMA:", " ".join(f"{n}={int(t[2,j,e])-t0}" for e, n in enumerate(names_mma)))
+    print(f"      MMA0:", " ".join(f"{n}={int(t[2,j,e])-t0}" for e, n in enumerate(names_mma)))
+    print(f"      MMA1:", " ".join(f"{n}={int(t[3,j,e])-t0}" for e, n in enumerate(names_mma)))

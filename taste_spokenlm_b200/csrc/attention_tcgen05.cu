@@ -12,8 +12,8 @@
 // rescaled only when a row's maximum grows by more than 2^8 (the stale maximum keeps exp2 arguments <= 8, exact in
 // fp32 / bf16 range), so the O read-modify-write in TMEM is rare after the first key block.
 //
-// Roles (320 threads): warps 0-3 softmax tile 0, warps 4-7 softmax tile 1 (warp w owns TMEM lanes 32*(w%4)..+31),
-// warp 8 TMA producer, warp 9 MMA issuer + TMEM allocator.
+// Roles (352 threads): warps 0-3 softmax tile 0, warps 4-7 softmax tile 1 (warp w owns TMEM lanes 32*(w%4)..+31),
+// warp 8 TMA producer, warp 9 MMA issuer of tile 0 + TMEM allocator, warp 10 MMA issuer of tile 1.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -21,16 +21,17 @@
 
 namespace taste {
 
-constexpr int FA_BQ = 128;          // query rows per tile (2 tiles per CTA)
+constexpr int FA_BQ = 128;          // query rows per tile (2 tiles per work item)
 constexpr int FA_BK = 128;          // keys per block
 constexpr int FA_HD = 64;
 constexpr int FA_STAGES = 4;
-constexpr int FA_THREADS = 320;
+constexpr int FA_THREADS = 352;
 #ifndef FA_POLY
-#define FA_POLY 7                   // of every 16 score pairs, this many take the polynomial exp2 path
+#define FA_POLY 4                   // of every 16 score pairs, this many take the polynomial exp2 path
 #endif
 constexpr uint32_t FA_TILE_BYTES = FA_BQ * FA_HD * 2;      // 16 KB: one Q, K or V tile
-constexpr size_t FA_SMEM = 1024 + size_t(2 + 2 * FA_STAGES) * FA_TILE_BYTES + 256;
+// Q is double buffered (2 x 2 tiles) so the next work item's queries load under the current item's last blocks
+constexpr size_t FA_SMEM = 1024 + size_t(4 + 2 * FA_STAGES) * FA_TILE_BYTES + 256;
 
 // TMEM columns
 constexpr uint32_t FA_COL_S = 0;      // S0 [0,128)  S1 [128,256)
@@ -42,47 +43,54 @@ struct FaParams {
   __nv_bfloat16* o;
   int ldo;
   int q_len, kv_len;
+  int heads, q_blocks, n_items;      // work item w = (b * heads + head) * q_blocks + qb
 };
 
-#define FA_TRACE(slot, idx)                                                                         \
-  do {                                                                                              \
-    if (VAR == 4 && p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0)   \
-      p.dbg[(slot) * 256 + (idx)] = clock64();                                                     \
+#define FA_TRACE(slot, idx)                                                      \
+  do {                                                                           \
+    if (VAR == 4 && p.dbg && blockIdx.x == 0 && lane == 0 && (idx) < 256)        \
+      p.dbg[(slot) * 256 + (idx)] = clock64();                                   \
   } while (0)
 
-template <int VAR>
+// Persistent: one CTA per SM loops over work items (256 queries of one (utterance, head)); TMEM, barriers and the
+// K/V ring live across items, the next item's Q / K / V loads and first QK^T run under the current item's tail, so
+// the ~4 us of per-CTA set-up and drain measured on the non-persistent version is paid once per launch.
+template <int VAR, int POLY>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                          const __grid_constant__ CUtensorMap tma_v, const FaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                                   // 2 tiles
-  uint8_t* sKV = smem + 2 * FA_TILE_BYTES;              // FA_STAGES x {K, V}
+  uint8_t* sQ = smem;                                   // 2 buffers x 2 tiles
+  uint8_t* sKV = smem + 4 * FA_TILE_BYTES;              // FA_STAGES x {K, V}
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + size_t(2 * FA_STAGES) * FA_TILE_BYTES);
-  uint64_t* q_full = bars;                              // [1]
-  uint64_t* kv_full = bars + 1;                         // [FA_STAGES]
+  uint64_t* q_full = bars;                              // [2]
+  uint64_t* q_empty = bars + 2;                         // [2]  all QK^T of the item retired (MMA -> producer)
+  uint64_t* kv_full = bars + 4;                         // [FA_STAGES]
   uint64_t* kv_empty = kv_full + FA_STAGES;             // [FA_STAGES]
-  uint64_t* s_full = kv_empty + FA_STAGES;              // [2]  S_i ready            (MMA -> softmax)
-  uint64_t* s_free = s_full + 2;                        // [2]  S_i copied to registers (softmax -> MMA), 4 warp arrivals
-  uint64_t* p_full = s_free + 2;                        // [2]  P_i written           (softmax -> MMA), 4 warp arrivals
-  uint64_t* o_full = p_full + 2;                        // [2]  P_i V done            (MMA -> softmax)
+  uint64_t* s_full = kv_empty + FA_STAGES;              // [2]  S_i ready               (MMA -> softmax)
+  uint64_t* s_free = s_full + 2;                        // [2]  S_i read from TMEM      (softmax -> MMA), 4 warp arrivals
+  uint64_t* p_full = s_free + 2;                        // [2]  P_i written             (softmax -> MMA), 4 warp arrivals
+  uint64_t* o_full = p_full + 2;                        // [2]  P_i V done              (MMA -> softmax)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int b = blockIdx.z;
-  const int head = blockIdx.y;
-  const int q0 = blockIdx.x * (2 * FA_BQ);
   const int n_blocks = (p.kv_len + FA_BK - 1) / FA_BK;
+  const int my_items = (p.n_items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  const int total_g = my_items * n_blocks;              // key blocks this CTA walks through, over all its items
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tma_q);
     tma_prefetch_desc(&tma_k);
     tma_prefetch_desc(&tma_v);
-    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 2);            // one tcgen05.commit per MMA issuer
+    }
     for (int s = 0; s < FA_STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
+      mbar_init(&kv_empty[s], 2);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
@@ -105,34 +113,51 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
   // `if (lane == 0)` region every UTCHMMA is wrapped in an ELECT loop: ~90 cycles per MMA, measured with FA_TRACE).
   if (warp == 8) {
     // ===================== TMA producer =====================
-    if (elect_one()) {
-      mbar_expect_tx(q_full, 2 * FA_TILE_BYTES);
-      tma_load_3d(sQ, &tma_q, q_full, head * FA_HD, q0, b);
-      tma_load_3d(sQ + FA_TILE_BYTES, &tma_q, q_full, head * FA_HD, q0 + FA_BQ, b);
-    }
-    __syncwarp();
     int stage = 0;
     uint32_t phase = 0;
-    for (int j = 0; j < n_blocks; ++j) {
-      mbar_wait_relaxed(&kv_empty[stage], phase ^ 1);
-      uint8_t* sk = sKV + size_t(2 * stage) * FA_TILE_BYTES;
+    for (int it = 0; it < my_items; ++it) {
+      const int w = int(blockIdx.x) + it * int(gridDim.x);
+      const int qb = w % p.q_blocks;
+      const int bh = w / p.q_blocks;
+      const int head = bh % p.heads;
+      const int b = bh / p.heads;
+      const int q0 = qb * (2 * FA_BQ);
+      const int qbuf = it & 1;
+      mbar_wait_relaxed(&q_empty[qbuf], uint32_t(((it >> 1) & 1) ^ 1));
       if (elect_one()) {
-        mbar_expect_tx(&kv_full[stage], 2 * FA_TILE_BYTES);
-        tma_load_3d(sk, &tma_k, &kv_full[stage], head * FA_HD, j * FA_BK, b);
-        tma_load_3d(sk + FA_TILE_BYTES, &tma_v, &kv_full[stage], head * FA_HD, j * FA_BK, b);
+        uint8_t* sq = sQ + size_t(2 * qbuf) * FA_TILE_BYTES;
+        mbar_expect_tx(&q_full[qbuf], 2 * FA_TILE_BYTES);
+        tma_load_3d(sq, &tma_q, &q_full[qbuf], head * FA_HD, q0, b);
+        tma_load_3d(sq + FA_TILE_BYTES, &tma_q, &q_full[qbuf], head * FA_HD, q0 + FA_BQ, b);
       }
       __syncwarp();
-      if (++stage == FA_STAGES) {
-        stage = 0;
-        phase ^= 1;
+      for (int j = 0; j < n_blocks; ++j) {
+        mbar_wait_relaxed(&kv_empty[stage], phase ^ 1);
+        uint8_t* sk = sKV + size_t(2 * stage) * FA_TILE_BYTES;
+        if (elect_one()) {
+          mbar_expect_tx(&kv_full[stage], 2 * FA_TILE_BYTES);
+          tma_load_3d(sk, &tma_k, &kv_full[stage], head * FA_HD, j * FA_BK, b);
+          tma_load_3d(sk + FA_TILE_BYTES, &tma_v, &kv_full[stage], head * FA_HD, j * FA_BK, b);
+        }
+        __syncwarp();
+        if (++stage == FA_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
     }
-  } else if (warp == 9) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 9 || warp == 10) {
+    // ===================== MMA issuers: warp 9 drives query tile 0, warp 10 tile 1 =====================
+    // One issuing thread per tile, so neither tile's GEMMs ever queue behind a barrier that only the other tile's
+    // softmax warps can satisfy (with a single issuer and a fixed wait order the two warpgroups throttled each other).
+    const int i = warp - 9;
     constexpr uint32_t idesc_qk = umma_idesc(FA_BQ, FA_BK, 1, 0, 0);        // A, B K-major
     constexpr uint32_t idesc_pv = umma_idesc(FA_BQ, FA_HD, 1, 0, 1);        // A from TMEM, B (V) MN-major
-    auto issue_qk = [&](int i, int stage) {
-      const uint64_t da = umma_desc_k_sw128(smem_u32(sQ + size_t(i) * FA_TILE_BYTES));
+    // S_i = Q_i K^T for global block index g (item g / n_blocks, key block g % n_blocks)
+    auto issue_qk = [&](int g) {
+      const int qbuf = (g / n_blocks) & 1;
+      const int stage = g % FA_STAGES;
+      const uint64_t da = umma_desc_k_sw128(smem_u32(sQ + size_t(2 * qbuf + i) * FA_TILE_BYTES));
       const uint64_t db = umma_desc_k_sw128(smem_u32(sKV + size_t(2 * stage) * FA_TILE_BYTES));
       if (elect_one()) {
 #pragma unroll
@@ -143,200 +168,222 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
       }
       __syncwarp();
     };
-    mbar_wait(q_full, 0);
-    mbar_wait(&kv_full[0], 0);
-    tc_fence_after();
-    issue_qk(0, 0);
-    int stage = 0;
-    uint32_t phase = 0;          // phase of kv_full[stage] for block j
-    for (int j = 0; j < n_blocks; ++j) {
-      int nstage = stage + 1;
-      uint32_t nphase = phase;
-      if (nstage == FA_STAGES) {
-        nstage = 0;
-        nphase ^= 1;
-      }
-      const bool more = j + 1 < n_blocks;
+    // everything block g needs from the producer: its K/V stage and, on the first block of an item, the item's Q
+    auto wait_inputs = [&](int g) {
+      const int it = g / n_blocks;
+      if (g % n_blocks == 0) mbar_wait(&q_full[it & 1], uint32_t((it >> 1) & 1));
+      mbar_wait(&kv_full[g % FA_STAGES], uint32_t((g / FA_STAGES) & 1));
+      tc_fence_after();
+    };
+    if (total_g > 0) {
+      wait_inputs(0);
+      // tile 1 starts half a block behind tile 0 (when tile 0's first S tile has been read), so that one warpgroup
+      // is in its exp2-heavy pass while the other reads / reduces scores instead of both hitting the MUFU together
+      if (i == 1) mbar_wait(&s_free[0], 0);
+      issue_qk(0);
+    }
+    for (int g = 0; g < total_g; ++g) {
+      const int j = g % n_blocks;
+      const int stage = g % FA_STAGES;
+      const bool more = g + 1 < total_g;
       const uint64_t dv = umma_desc_mn_sw128(smem_u32(sKV + size_t(2 * stage + 1) * FA_TILE_BYTES), 0);
-      auto issue_pv = [&](int i, bool release_kv) {
-        if (elect_one()) {
+      if (more) wait_inputs(g + 1);
+      mbar_wait(&s_free[i], uint32_t(g & 1));
+      FA_TRACE(2 + i, g * 8 + 0);
+      tc_fence_after();
+      if (more) issue_qk(g + 1);          // next block's scores first: the softmax warps wait on these
+      FA_TRACE(2 + i, g * 8 + 1);
+      mbar_wait(&p_full[i], uint32_t(g & 1));
+      FA_TRACE(2 + i, g * 8 + 2);
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < FA_BK / 16; ++k)     // 16 keys per MMA: 8 TMEM columns of P, 2048 B of V
-            umma_ts(tmem_base + FA_COL_O + uint32_t(i * FA_HD), tmem_base + FA_COL_P + uint32_t(i * 64 + k * 8),
-                    dv + uint64_t(k * (2048 >> 4)), idesc_pv, (j | k) != 0 ? 1u : 0u);
-          umma_commit(&o_full[i]);
-          if (release_kv) umma_commit(&kv_empty[stage]);
-        }
-        __syncwarp();
-      };
-      // The two warpgroups run half a block apart (tile 1 starts when tile 0 is half way through its first
-      // block), so one is in its exp2-heavy pass while the other reads / reduces its scores.  The waits below
-      // follow that order of events: S0 copied, P0 written, S1 copied, P1 written.
-      if (more) mbar_wait(&kv_full[nstage], nphase);
-      mbar_wait(&s_free[0], uint32_t(j & 1));
-      FA_TRACE(2, j * 8 + 0);
-      tc_fence_after();
-      if (more) issue_qk(0, nstage);
-      if (j == 0) issue_qk(1, 0);
-      FA_TRACE(2, j * 8 + 1);
-      mbar_wait(&p_full[0], uint32_t(j & 1));
-      FA_TRACE(2, j * 8 + 2);
-      tc_fence_after();
-      issue_pv(0, false);
-      FA_TRACE(2, j * 8 + 3);
-      mbar_wait(&s_free[1], uint32_t(j & 1));
-      FA_TRACE(2, j * 8 + 4);
-      tc_fence_after();
-      if (more) issue_qk(1, nstage);
-      mbar_wait(&p_full[1], uint32_t(j & 1));
-      FA_TRACE(2, j * 8 + 5);
-      tc_fence_after();
-      issue_pv(1, true);
-      FA_TRACE(2, j * 8 + 6);
-      stage = nstage;
-      phase = nphase;
+        for (int k = 0; k < FA_BK / 16; ++k)     // 16 keys per MMA: 8 TMEM columns of P, 2048 B of V
+          umma_ts(tmem_base + FA_COL_O + uint32_t(i * FA_HD), tmem_base + FA_COL_P + uint32_t(i * 64 + k * 8),
+                  dv + uint64_t(k * (2048 >> 4)), idesc_pv, (j | k) != 0 ? 1u : 0u);
+        umma_commit(&o_full[i]);
+        umma_commit(&kv_empty[stage]);                                   // needs both tiles' commits
+        if (j == n_blocks - 1) umma_commit(&q_empty[(g / n_blocks) & 1]);   // likewise
+      }
+      __syncwarp();
+      FA_TRACE(2 + i, g * 8 + 3);
     }
   } else {
     // ===================== softmax + output (warps 0-7) =====================
     const int i = warp >> 2;                        // query tile
     const int q = warp & 3;                         // TMEM lane quarter
-    const int row = q0 + i * FA_BQ + q * 32 + lane; // query index within the utterance
     const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16);
     const uint32_t t_s = lane_base + FA_COL_S + uint32_t(i * FA_BK);
     const uint32_t t_o = lane_base + FA_COL_O + uint32_t(i * FA_HD);
     const uint32_t t_p = lane_base + FA_COL_P + uint32_t(i * 64);
     const float kLog2e = 1.4426950408889634f;
-    float m_used = -INFINITY;      // stale running maximum (raw score units)
-    float l_run = 0.f;
+    int g = 0;
+    for (int it = 0; it < my_items; ++it) {
+      const int w = int(blockIdx.x) + it * int(gridDim.x);
+      const int qb = w % p.q_blocks;
+      const int bh = w / p.q_blocks;
+      const int head = bh % p.heads;
+      const int b = bh / p.heads;
+      const int row = qb * (2 * FA_BQ) + i * FA_BQ + q * 32 + lane;   // query index within the utterance
+      float m_used = -INFINITY;      // stale running maximum (raw score units)
+      float l_run = 0.f;
+      bool pending = false;          // P of the previous block written but not yet signalled
 
-    for (int j = 0; j < n_blocks; ++j) {
-      FA_TRACE(i, j * 8 + 0);
-      mbar_wait(&s_full[i], uint32_t(j & 1));
-      FA_TRACE(i, j * 8 + 1);
-      tc_fence_after();
-      // The S tile is read twice from TMEM in 32-column chunks (pass 1: row maximum, pass 2: exponentials), always
-      // with the NEXT chunk's tcgen05.ld in flight while the current one is processed, so only the first load of a
-      // block exposes the TMEM latency.  Live registers: two chunks (64 scores) + 32 packed probabilities.
-      const int valid = p.kv_len - j * FA_BK;       // keys of this block that exist
-      uint32_t r[2][32];
-      float mx = -INFINITY;
-      tmem_ld_32x32b_x32(t_s, r[0]);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        tmem_ld_wait();
-        tmem_ld_32x32b_x32(t_s + uint32_t(((c + 1) & 3) * 32), r[(c + 1) & 1]);   // c == 3: chunk 0 again, for pass 2
-        if (valid < FA_BK) {
-#pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (c * 32 + e >= valid) r[c & 1][e] = 0xff800000u;      // -inf
-        }
-#pragma unroll
-        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(r[c & 1][e]));
-      }
-      FA_TRACE(i, j * 8 + 2);
-      const bool grow = mx > m_used + 5.545177f;     // 8 in log2 units; first block: m_used = -inf
-      const bool any_grow = __any_sync(0xffffffffu, grow);
-      float alpha = 1.0f;
-      if (any_grow) {
-        const float m_new = grow ? mx : m_used;
-        alpha = (m_used == -INFINITY) ? 0.f : fast_exp2((m_used - m_new) * kLog2e);
-        l_run *= alpha;
-        m_used = m_new;
-      }
-      // pass 2: p = exp2(s * log2e - m * log2e), row sum, bf16 P back to TMEM
-      const float neg_m = -m_used * kLog2e;
-      const uint64_t negm2 = f2_pack(neg_m, neg_m);
-      const uint64_t log2e2 = f2_pack(kLog2e, kLog2e);
-      uint64_t sum2 = f2_pack(0.f, 0.f);
-      uint32_t pk[32];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        tmem_ld_wait();
-        if (c < 3) {
-          tmem_ld_32x32b_x32(t_s + uint32_t((c + 1) * 32), r[(c + 1) & 1]);
-        } else {                                     // every read of S has landed: the next block's QK^T may overwrite it
+      for (int j = 0; j < n_blocks; ++j, ++g) {
+        FA_TRACE(i, g * 8 + 0);
+        mbar_wait(&s_full[i], uint32_t(g & 1));
+        FA_TRACE(i, g * 8 + 1);
+        tc_fence_after();
+        // The S tile is read twice from TMEM in 32-column chunks (pass 1: row maximum, pass 2: exponentials).
+        // tcgen05.wait::ld waits for every load in flight, so the loads are grouped to expose the TMEM latency only
+        // about three times per block: {c0,c1,c2} -> one wait; {c3, c0 again} under the maxima of c1,c2 -> one wait;
+        // pass 2 then always has the next chunk in flight while it exponentiates the current one.
+        // (A speculative single pass against the stale maximum was tried and rejected: on high-variance scores a warp
+        // has to redo most early blocks.)
+        const int valid = p.kv_len - j * FA_BK;       // keys of this block that exist
+        uint32_t ra[32], rb[32], pk[32];              // pk: third load buffer in pass 1, packed probabilities in pass 2
+        tmem_ld_32x32b_x32(t_s, ra);
+        tmem_ld_32x32b_x32(t_s + 32, rb);
+        if (pending) {
+          // P of the previous block: its stores (sourced from pk) are waited for only now, under the latency of the
+          // loads above, and before pk is reused as a load destination
+          tmem_st_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&s_free[i]);
-          FA_TRACE(i, j * 8 + 3);
+          if (lane == 0) mbar_arrive(&p_full[i]);
+          pending = false;
         }
-        if (valid < FA_BK) {
+        tmem_ld_32x32b_x32(t_s + 64, pk);
+        tmem_ld_wait();
+        auto mask_chunk = [&](uint32_t (&x)[32], int c) {
+          if (valid < FA_BK) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (c * 32 + e >= valid) r[c & 1][e] = 0xff800000u;
-        }
-        // Exponentials in pairs (packed FFMA2 / FADD2).  16/clk/SM of MUFU.EX2 would cap the tensor pipe at 50 %, so
-        // FA_POLY of every 16 pairs are evaluated on the FMA pipe instead (exp2_poly2).
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const uint64_t t2 = f2_fma(f2_pack(__uint_as_float(r[c & 1][2 * e]), __uint_as_float(r[c & 1][2 * e + 1])),
-                                     log2e2, negm2);
-          float p0, p1;
-          if (((e * FA_POLY) & 15) < FA_POLY && FA_POLY > 0) {       // evenly spread FA_POLY of 16
-            exp2_poly2(t2, p0, p1);
-          } else {
-            f2_unpack(t2, p0, p1);
-            p0 = fast_exp2(p0);
-            p1 = fast_exp2(p1);
+            for (int e = 0; e < 32; ++e)
+              if (c * 32 + e >= valid) x[e] = 0xff800000u;      // -inf
           }
-          sum2 = f2_add(sum2, f2_pack(p0, p1));
-          pk[(c & 1) * 16 + e] = pack_bf16x2(p0, p1);
+        };
+        float mx = -INFINITY;
+        mask_chunk(ra, 0);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(ra[e]));
+        tmem_ld_32x32b_x32(t_s + 96, ra);              // c3
+        mask_chunk(rb, 1);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(rb[e]));
+        tmem_ld_32x32b_x32(t_s, rb);                   // c0 again, for pass 2
+        mask_chunk(pk, 2);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(pk[e]));
+        tmem_ld_wait();
+        mask_chunk(ra, 3);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(ra[e]));
+        FA_TRACE(i, g * 8 + 2);
+        const bool grow = mx > m_used + 5.545177f;     // 8 in log2 units; first block: m_used = -inf
+        const bool any_grow = __any_sync(0xffffffffu, grow);
+        float alpha = 1.0f;
+        if (any_grow) {
+          const float m_new = grow ? mx : m_used;
+          alpha = (m_used == -INFINITY) ? 0.f : fast_exp2((m_used - m_new) * kLog2e);
+          l_run *= alpha;
+          m_used = m_new;
         }
-        if (c == 1 && j > 0) {
-          // Only now is the previous block's P V needed: P_i has been consumed (it may be overwritten) and O_i is
-          // stable (it may be rescaled).
- FA_TRACE(i, j * 8 + 4);
-          mbar_wait(&o_full[i], uint32_t((j - 1) & 1));
-          FA_TRACE(i, j * 8 + 5);
-          tc_fence_after();
-          if (any_grow) {
-            tmem_ld_wait();                          // drain the in-flight S chunk before reusing the wait below
+        // pass 2: p = exp2(s * log2e - m * log2e), row sum, bf16 P back to TMEM.  Chunk c lives in rb (c even) / ra (c odd)
+        const float neg_m = -m_used * kLog2e;
+        const uint64_t negm2 = f2_pack(neg_m, neg_m);
+        const uint64_t log2e2 = f2_pack(kLog2e, kLog2e);
+        uint64_t sum2 = f2_pack(0.f, 0.f);
 #pragma unroll
-            for (int cc = 0; cc < FA_HD / 32; ++cc) {
-              uint32_t o[32];
-              tmem_ld_32x32b_x32(t_o + uint32_t(cc * 32), o);
-              tmem_ld_wait();
+        for (int c = 0; c < 4; ++c) {
+          uint32_t (&cur)[32] = (c & 1) ? ra : rb;
+          uint32_t (&nxt)[32] = (c & 1) ? rb : ra;
+          if (c > 0) tmem_ld_wait();
+          if (c < 3) {
+            tmem_ld_32x32b_x32(t_s + uint32_t((c + 1) * 32), nxt);
+          } else {                                     // every read of S has landed: the next QK^T may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[i]);
+            FA_TRACE(i, g * 8 + 3);
+          }
+          mask_chunk(cur, c);
+          // Exponentials in pairs (packed FFMA2 / FADD2).  16/clk/SM of MUFU.EX2 would cap the tensor pipe at 50 %,
+          // so POLY of every 16 pairs are evaluated on the FMA pipe instead (exp2_poly2).
 #pragma unroll
-              for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-              tmem_st_32x32b_x32(t_o + uint32_t(cc * 32), o);
+          for (int e = 0; e < 16; ++e) {
+            const uint64_t t2 = f2_fma(f2_pack(__uint_as_float(cur[2 * e]), __uint_as_float(cur[2 * e + 1])), log2e2, negm2);
+            float p0, p1;
+            if (((e * POLY) & 15) < POLY && POLY > 0) {       // evenly spread POLY of 16
+              exp2_poly2(t2, p0, p1);
+            } else {
+              f2_unpack(t2, p0, p1);
+              p0 = fast_exp2(p0);
+              p1 = fast_exp2(p1);
+            }
+            sum2 = f2_add(sum2, f2_pack(p0, p1));
+            pk[(c & 1) * 16 + e] = pack_bf16x2(p0, p1);
+          }
+          if (c == 1 && j > 0) {
+            // Only now is the previous block's P V needed: P_i has been consumed (it may be overwritten) and O_i is
+            // stable (it may be rescaled).  On the first block of an item the output pass below already waited.
+            FA_TRACE(i, g * 8 + 4);
+            mbar_wait(&o_full[i], uint32_t((g - 1) & 1));
+            FA_TRACE(i, g * 8 + 5);
+            tc_fence_after();
+            if (any_grow) {
+              tmem_ld_wait();                          // drain the in-flight S chunk before reusing the wait below
+#pragma unroll
+              for (int cc = 0; cc < FA_HD / 32; ++cc) {
+                uint32_t o[32];
+                tmem_ld_32x32b_x32(t_o + uint32_t(cc * 32), o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+                tmem_st_32x32b_x32(t_o + uint32_t(cc * 32), o);
+              }
             }
           }
+          if (c & 1) tmem_st_32x32b_x32(t_p + uint32_t((c >> 1) * 32), pk);
         }
-        if (c & 1) tmem_st_32x32b_x32(t_p + uint32_t((c >> 1) * 32), pk);
+        float sum0, sum1;
+        f2_unpack(sum2, sum0, sum1);
+        l_run += sum0 + sum1;
+        if (j + 1 < n_blocks) {
+          pending = true;              // the P stores are waited for (and p_full signalled) under the next block's loads
+        } else {
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[i]);
+        }
+        FA_TRACE(i, g * 8 + 6);
       }
-      float sum0, sum1;
-      f2_unpack(sum2, sum0, sum1);
-      const float sum = sum0 + sum1;
-      l_run += sum;
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[i]);
-      FA_TRACE(i, j * 8 + 6);
-    }
 
-    // ---- output: O_i / l ----
-    mbar_wait(&o_full[i], uint32_t((n_blocks - 1) & 1));
-    tc_fence_after();
-    const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-    __nv_bfloat16* orow = p.o + (int64_t(b) * p.q_len + row) * p.ldo + head * FA_HD;
+      // ---- output: O_i / l ----
+      mbar_wait(&o_full[i], uint32_t((g - 1) & 1));
+      tc_fence_after();
+      const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+      __nv_bfloat16* orow = p.o + (int64_t(b) * p.q_len + row) * p.ldo + head * FA_HD;
 #pragma unroll
-    for (int c = 0; c < FA_HD / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(t_o + uint32_t(c * 32), r);
-      tmem_ld_wait();
-      if (row < p.q_len) {
-        uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+      for (int c = 0; c < FA_HD / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_o + uint32_t(c * 32), r);
+        tmem_ld_wait();
+        if (row < p.q_len) {
+          uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(r[8 * e + 0]) * inv, __uint_as_float(r[8 * e + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(r[8 * e + 2]) * inv, __uint_as_float(r[8 * e + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(r[8 * e + 4]) * inv, __uint_as_float(r[8 * e + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(r[8 * e + 6]) * inv, __uint_as_float(r[8 * e + 7]) * inv);
-          dst[e] = u;
+          for (int e = 0; e < 4; ++e) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(r[8 * e + 0]) * inv, __uint_as_float(r[8 * e + 1]) * inv);
+            u.y = pack_bf16x2(__uint_as_float(r[8 * e + 2]) * inv, __uint_as_float(r[8 * e + 3]) * inv);
+            u.z = pack_bf16x2(__uint_as_float(r[8 * e + 4]) * inv, __uint_as_float(r[8 * e + 5]) * inv);
+            u.w = pack_bf16x2(__uint_as_float(r[8 * e + 6]) * inv, __uint_as_float(r[8 * e + 7]) * inv);
+            dst[e] = u;
+          }
         }
       }
+      tc_fence_before();      // O_i has been read: the next item's first P V (accumulate = 0) may overwrite it; that MMA
+                              // is issued only after this warpgroup's next p_full arrive, which follows in program order
     }
   }
   tc_fence_before();
@@ -399,8 +446,9 @@ int launch_attention_tcgen05(const AttnDesc& d, cudaStream_t stream) {
   if ((rc = make_map(enc, &mv, d.v, d.heads, d.kv_len, d.batch, d.ldv))) return rc;
   static bool configured = false;
   if (!configured) {
-    TASTE_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM));
-    TASTE_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM));
+#define FA_CFG(V, P) TASTE_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<V, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM))
+    FA_CFG(0, FA_POLY); FA_CFG(4, FA_POLY); FA_CFG(0, 0); FA_CFG(0, 7); FA_CFG(0, 10);
+#undef FA_CFG
     configured = true;
   }
   const char* ev = getenv("TASTE_FA_VAR");
@@ -411,12 +459,27 @@ int launch_attention_tcgen05(const AttnDesc& d, cudaStream_t stream) {
   p.ldo = d.ldo;
   p.q_len = d.q_len;
   p.kv_len = d.kv_len;
-  dim3 grid((d.q_len + 2 * FA_BQ - 1) / (2 * FA_BQ), d.heads, d.batch);
+  p.heads = d.heads;
+  p.q_blocks = (d.q_len + 2 * FA_BQ - 1) / (2 * FA_BQ);
+  p.n_items = p.q_blocks * d.heads * d.batch;
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+  }
+  dim3 grid(p.n_items < n_sm ? p.n_items : n_sm);
   const double pairs = double(d.batch) * d.q_len * d.kv_len;
   ProfScope ps(stream, d.kclass == KC_ATTN_ENC ? KC_ATTN_ENC : KC_ATTN_TC, 4.0 * pairs * FA_HD * d.heads,
                2.0 * FA_HD * d.heads * double(d.batch) * (2.0 * d.q_len + 2.0 * d.kv_len));
-  if (var == 4) attention_tcgen05_kernel<4><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
-  else attention_tcgen05_kernel<0><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
+  const char* ep = getenv("TASTE_FA_POLY");          // experiment knob: 0 / 7 / 10 of every 16 pairs on the FMA pipe
+  const int poly = ep ? atoi(ep) : FA_POLY;
+  if (var == 4) attention_tcgen05_kernel<4, FA_POLY><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
+  else if (poly == 0) attention_tcgen05_kernel<0, 0><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
+  else if (poly == 7) attention_tcgen05_kernel<0, 7><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
+  else if (poly == 10) attention_tcgen05_kernel<0, 10><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
+  else attention_tcgen05_kernel<0, FA_POLY><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
   TASTE_CUDA_OK(cudaGetLastError());
   return 0;
 }
