@@ -156,7 +156,7 @@ def run_reference_arm(args, rank):
     v = args.steps * UTT_SECONDS / dt
     cores = os.cpu_count() or 1
     sample = f"1 utterance (30 s, {args.tokens} tokens) of the batch-64 workload per step, fp32, torch CPU, {cores} threads"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -164,7 +164,7 @@ def run_reference_arm(args, rank):
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 def workload_config(args, world, cpu=False):
@@ -180,7 +180,27 @@ def workload_config(args, world, cpu=False):
 # ---------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Everything native libraries print to fd 1 (e.g. NCCL's version banner) goes to stderr; the single JSON line is
+    written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
@@ -253,8 +273,9 @@ def main():
         counts = torch.tensor([int(batch["lengths_host"].sum())], device=dev, dtype=torch.int64)
         all_counts = torch.empty(world, dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(all_counts, counts)
-        all_idx = torch.empty(world * idx.numel(), dtype=torch.int16, device=dev)
-        dist.all_gather_into_tensor(all_idx, idx.to(torch.int16).reshape(-1))
+        packed = idx.to(torch.int16).reshape(-1).view(torch.uint8)       # NCCL has no int16: move the raw bytes
+        all_idx = torch.empty(world * packed.numel(), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(all_idx, packed)
     e1.record()
     barrier()
     t_wall1 = time.time()
@@ -370,7 +391,7 @@ def main():
     }
     if args.layers != 32:
         line["INVALID"] = "debug run with a reduced layer count; not the named config"
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
