@@ -211,6 +211,7 @@ def main():
     ap.add_argument("--layers", type=int, default=32, help="encoder layers (32 = the named config; others are for debugging and flagged)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--encoder-mode", type=int, default=0, help="taste_encoder_set_mode (A/B runs): 0 default, 1 no LayerNorm folding, 2 fold both")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -235,6 +236,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    _lib.check(lib.taste_encoder_set_mode(args.encoder_mode), "taste_encoder_set_mode")
 
     cfg = synth.FULL if args.layers == synth.FULL.enc_layers else synth.TowerConfig(enc_layers=args.layers)
     torch.set_grad_enabled(False)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TASTE_ABI_VERSION 1
+#define TASTE_ABI_VERSION 2
 
 #define TASTE_E_ARG        (-1)  /* null pointer / bad size */
 #define TASTE_E_SHAPE      (-2)  /* geometry not supported by the kernels (see taste_handle_create) */
@@ -70,6 +70,11 @@ typedef struct {
   const float* ln2_w;  const float* ln2_b;     /* final_layer_norm */
   const void*  w1;     const float* b1;        /* fc1 [FF, D] */
   const void*  w2;     const float* b2;        /* fc2 [D, FF] */
+  /* Optional LayerNorm-folded copies (all six or none).  With them the encoder never materialises LayerNorm(h): the
+   * QKV / fc1 GEMMs read the raw bf16 rows and apply  rstd * (acc - mean * c[n]) + b'[n]  in their epilogue, with
+   *   W'[n][k] = W[n][k] * ln_w[k]  (bf16),  c[n] = sum_k W'[n][k],  b'[n] = b[n] + sum_k W[n][k] * ln_b[k].      */
+  const void*  wqkv_ln;  const float* bqkv_ln;  const float* cqkv_ln;     /* self_attn_layer_norm folded into QKV */
+  const void*  w1_ln;    const float* b1_ln;    const float* c1_ln;       /* final_layer_norm folded into fc1 */
 } taste_enc_layer_t;
 
 /* One aggregator (Whisper decoder) layer (CW:719-833). */
@@ -189,6 +194,22 @@ int taste_map_to_llm_tokens(const int64_t* asr_indices, const int32_t* asr_word_
  * 3 = fp32 out.  Requires N % 128 == 0, K % 64 == 0. */
 int taste_gemm_bf16(const void* a, const void* w, const float* bias, void* out, int m, int n, int k, int epilogue,
                     void* stream);
+/* General form of taste_gemm_bf16 with the optional LayerNorm-folding operands (see taste_enc_layer_t):
+ *   producer: stats_out [m][n/128][2] fp32 and out_bf16 [m,n] (epilogue 2 only): also emits the bf16 copy of the fp32
+ *             output rows and their per-128-column (sum, sum of squares);
+ *   consumer: ln_stats [m][ln_nseg][2], ln_colsum [n], bias = b' (epilogue 0 or 1): applies the folded LayerNorm.
+ * Requires n % 256 == 0 (CTA-pair kernel).  Unused pointers are NULL. */
+typedef struct {
+  const void* a; const void* w; const float* bias; void* out;
+  int32_t m, n, k, epilogue;
+  const float* ln_stats; int32_t ln_nseg; int32_t reserved; const float* ln_colsum;
+  float* stats_out; void* out_bf16;
+} taste_gemm_ex_t;
+int taste_gemm_ex(const taste_gemm_ex_t* g, void* stream);
+/* Encoder option for A/B timing and tests: 0 = fold self_attn_layer_norm into the fc2 -> QKV GEMM pair when the folded
+ * weights are present and the batch has >= 2048 rows (final_layer_norm stays a kernel), 1 = always run the separate
+ * LayerNorm kernels, 2 = fold both LayerNorms (measured slower; A/B only). */
+int taste_encoder_set_mode(int mode);
 /* Tile-shape override for A/B timing and tests: 0 = automatic (CTA pairs, 256 x 256 tiles, when one wave of pair tiles
  * exists), 1 = always the single-CTA 128 x {256,128} kernel.  Process-wide. */
 int taste_gemm_set_mode(int mode);

@@ -29,7 +29,14 @@ class Dims(C.Structure):
 
 
 class EncLayer(C.Structure):
-    _fields_ = [(n, p) for n in ("ln1_w", "ln1_b", "wqkv", "bqkv", "wo", "bo", "ln2_w", "ln2_b", "w1", "b1", "w2", "b2")]
+    _fields_ = [(n, p) for n in ("ln1_w", "ln1_b", "wqkv", "bqkv", "wo", "bo", "ln2_w", "ln2_b", "w1", "b1", "w2", "b2",
+                                 "wqkv_ln", "bqkv_ln", "cqkv_ln", "w1_ln", "b1_ln", "c1_ln")]
+
+
+class GemmEx(C.Structure):
+    _fields_ = [("a", p), ("w", p), ("bias", p), ("out", p), ("m", C.c_int32), ("n", C.c_int32), ("k", C.c_int32),
+                ("epilogue", C.c_int32), ("ln_stats", p), ("ln_nseg", C.c_int32), ("reserved", C.c_int32),
+                ("ln_colsum", p), ("stats_out", p), ("out_bf16", p)]
 
 
 class DecLayer(C.Structure):
@@ -70,6 +77,8 @@ _SIGS = {
     "taste_rvq_decode_f32": (C.c_int, [p, p, C.c_int, C.c_int, p, p]),
     "taste_map_to_llm_tokens": (C.c_int, [p, p, p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, p, p]),
     "taste_gemm_bf16": (C.c_int, [p, p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, p]),
+    "taste_gemm_ex": (C.c_int, [C.POINTER(GemmEx), p]),
+    "taste_encoder_set_mode": (C.c_int, [C.c_int]),
     "taste_attention_set_mode": (C.c_int, [C.c_int]),
     "taste_gemm_set_mode": (C.c_int, [C.c_int]),
     "taste_layernorm_f32": (C.c_int, [p, p, p, p, C.c_int, C.c_int, C.c_int, p]),

@@ -49,8 +49,11 @@ struct EncWs {
   float* h;
   void* a;
   void* big;
+  void* hb;        // bf16 copy of h (LayerNorm folding)
+  float* stats;    // per row and 128-column segment: (sum, sum of squares) of h
   size_t bytes;
 };
+int g_encoder_mode = 0;
 EncWs carve_encoder(const taste_dims_t& d, int batch, void* ws) {
   Carver c(ws);
   EncWs e;
@@ -60,6 +63,8 @@ EncWs carve_encoder(const taste_dims_t& d, int batch, void* ws) {
   e.h = static_cast<float*>(c.take(rows * d.d_model * 4));
   e.a = c.take(rows * d.d_model * 2);
   e.big = c.take(rows * wide * 2);       // conv1 output [B*3000, D] == [B*1500, 2D] also fits (wide >= 3D)
+  e.hb = c.take(rows * d.d_model * 2);
+  e.stats = static_cast<float*>(c.take(rows * size_t(d.d_model / 128 + 1) * 2 * 4));
   e.bytes = c.off;
   return e;
 }
@@ -198,6 +203,14 @@ int taste_encoder_fwd(taste_handle_t h, const float* feats_f32, const void* feat
     g.epilogue = EPI_GELU_BF16;
     if ((rc = launch_gemm(g, stream))) return rc;
   }
+  // LayerNorm folding: available when every layer carries the folded weights, the shapes fit the CTA-pair kernel and
+  // the batch is large enough for it (>= 2048 rows); otherwise the separate LayerNorm kernel runs (small batches).
+  bool fold = g_encoder_mode != 1 && rows >= 2048 && D % 256 == 0 && d.ffn % 256 == 0 && d.enc_layers > 0;
+  for (int l = 0; l < d.enc_layers && fold; ++l) {
+    const taste_enc_layer_t& L = h->enc[l];
+    fold = L.wqkv_ln && L.bqkv_ln && L.cqkv_ln && L.w1_ln && L.b1_ln && L.c1_ln;
+  }
+  const int nseg = D / 128;
   {   // conv2 (k3, s2, p1) + GELU + positions: input viewed as [B, 1500, 2, D]; output frame j reads
       // frames 2j-1, 2j, 2j+1 = (j-1, phase 1), (j, phase 0), (j, phase 1)            JES:175-180
     GemmDesc g;
@@ -220,15 +233,53 @@ int taste_encoder_fwd(taste_handle_t h, const float* feats_f32, const void* feat
     g.ldc = D;
     g.epilogue = EPI_GELU_POS_F32;
     g.pos = w.enc_pos;
+    if (fold) {
+      g.stats_out = e.stats;
+      g.out_bf16 = e.hb;
+    }
     if ((rc = launch_gemm(g, stream))) return rc;
   }
+  auto gemm_ex = [&](const void* a, const void* wt, const float* bias, void* out, int n, int k, int epi,
+                     const float* ln_stats, const float* colsum, float* stats_out, void* out_bf16) -> int {
+    GemmDesc g;
+    g.a = a;
+    g.k_inner = k;
+    g.s_count = 1;
+    g.rows_in = rows;
+    g.rows_out = rows;
+    g.batches = 1;
+    g.s_stride = int64_t(k) * 2;
+    g.r_stride = int64_t(k) * 2;
+    g.b_stride = int64_t(rows) * k * 2;
+    g.taps = 1;
+    g.w = wt;
+    g.n = n;
+    g.bias = bias;
+    g.out = out;
+    g.ldc = n;
+    g.epilogue = epi;
+    g.ln_stats = ln_stats;
+    g.ln_nseg = ln_stats ? nseg : 0;
+    g.ln_colsum = colsum;
+    g.stats_out = stats_out;
+    g.out_bf16 = out_bf16;
+    return launch_gemm(g, stream);
+  };
   for (int l = 0; l < d.enc_layers; ++l) {
     const taste_enc_layer_t& L = h->enc[l];
     if (l == d.target_layer) {                                                       // JES:192-193
-      if ((rc = launch_cast_bf16(e.h, h_target_bf16, int64_t(rows) * D, stream))) return rc;
+      if (fold) {
+        TASTE_CUDA_OK(cudaMemcpyAsync(h_target_bf16, e.hb, size_t(rows) * D * 2, cudaMemcpyDeviceToDevice, stream));
+      } else if ((rc = launch_cast_bf16(e.h, h_target_bf16, int64_t(rows) * D, stream))) {
+        return rc;
+      }
     }
-    if ((rc = launch_layernorm(e.h, L.ln1_w, L.ln1_b, e.a, rows, D, true, stream))) return rc;              // CW:690
-    if ((rc = gemm_plain(e.a, L.wqkv, L.bqkv, e.big, rows, 3 * D, D, EPI_BF16, stream))) return rc;         // CW:342,365
+    if (fold) {
+      if ((rc = gemm_ex(e.hb, L.wqkv_ln, L.bqkv_ln, e.big, 3 * D, D, EPI_BF16, e.stats, L.cqkv_ln, nullptr, nullptr))) return rc;   // CW:690 + 342,365
+    } else {
+      if ((rc = launch_layernorm(e.h, L.ln1_w, L.ln1_b, e.a, rows, D, true, stream))) return rc;              // CW:690
+      if ((rc = gemm_plain(e.a, L.wqkv, L.bqkv, e.big, rows, 3 * D, D, EPI_BF16, stream))) return rc;         // CW:342,365
+    }
     AttnDesc at;
     at.q = e.big;
     at.k = static_cast<const uint16_t*>(e.big) + D;
@@ -243,10 +294,25 @@ int taste_encoder_fwd(taste_handle_t h, const float* feats_f32, const void* feat
     at.causal = 0;
     at.kclass = KC_ATTN_ENC;
     if ((rc = launch_attention(at, stream))) return rc;                                                      // CW:377-394
-    if ((rc = gemm_plain(e.a, L.wo, L.bo, e.h, rows, D, D, EPI_RESID_F32, stream))) return rc;              // CW:407,692
-    if ((rc = launch_layernorm(e.h, L.ln2_w, L.ln2_b, e.a, rows, D, true, stream))) return rc;              // CW:698
-    if ((rc = gemm_plain(e.a, L.w1, L.b1, e.big, rows, d.ffn, D, EPI_GELU_BF16, stream))) return rc;        // CW:699
-    if ((rc = gemm_plain(e.big, L.w2, L.b2, e.h, rows, D, d.ffn, EPI_RESID_F32, stream))) return rc;        // CW:701-703
+    if (fold && g_encoder_mode == 2) {
+      // both LayerNorms folded (measured slower than the hybrid below: the GELU epilogue of fc1 and the HBM-bound
+      // out_proj epilogue have no slack for the extra work; kept for A/B runs)
+      if ((rc = gemm_ex(e.a, L.wo, L.bo, e.h, D, D, EPI_RESID_F32, nullptr, nullptr, e.stats, e.hb))) return rc;            // CW:407,692
+      if ((rc = gemm_ex(e.hb, L.w1_ln, L.b1_ln, e.big, d.ffn, D, EPI_GELU_BF16, e.stats, L.c1_ln, nullptr, nullptr))) return rc;   // CW:698-699
+      if ((rc = gemm_ex(e.big, L.w2, L.b2, e.h, D, d.ffn, EPI_RESID_F32, nullptr, nullptr, e.stats, e.hb))) return rc;      // CW:701-703
+    } else if (fold) {
+      // hybrid: self_attn_layer_norm is folded (producer = fc2 with K = 5120, whose epilogue has slack; consumer = the
+      // QKV GEMM, whose bias-only epilogue has slack); final_layer_norm stays a kernel
+      if ((rc = gemm_plain(e.a, L.wo, L.bo, e.h, rows, D, D, EPI_RESID_F32, stream))) return rc;                            // CW:407,692
+      if ((rc = launch_layernorm(e.h, L.ln2_w, L.ln2_b, e.a, rows, D, true, stream))) return rc;                            // CW:698
+      if ((rc = gemm_plain(e.a, L.w1, L.b1, e.big, rows, d.ffn, D, EPI_GELU_BF16, stream))) return rc;                      // CW:699
+      if ((rc = gemm_ex(e.big, L.w2, L.b2, e.h, D, d.ffn, EPI_RESID_F32, nullptr, nullptr, e.stats, e.hb))) return rc;      // CW:701-703
+    } else {
+      if ((rc = gemm_plain(e.a, L.wo, L.bo, e.h, rows, D, D, EPI_RESID_F32, stream))) return rc;              // CW:407,692
+      if ((rc = launch_layernorm(e.h, L.ln2_w, L.ln2_b, e.a, rows, D, true, stream))) return rc;              // CW:698
+      if ((rc = gemm_plain(e.a, L.w1, L.b1, e.big, rows, d.ffn, D, EPI_GELU_BF16, stream))) return rc;        // CW:699
+      if ((rc = gemm_plain(e.big, L.w2, L.b2, e.h, rows, D, d.ffn, EPI_RESID_F32, stream))) return rc;        // CW:701-703
+    }
   }
   if (d.target_layer >= d.enc_layers) return set_error(TASTE_E_SHAPE, "encoder_fwd: target layer not reached");
   return launch_layernorm(e.h, w.enc_ln_w, w.enc_ln_b, h_last_bf16, rows, D, true, stream);                 // JES:211
@@ -355,6 +421,40 @@ int taste_gemm_bf16(const void* a, const void* w, const float* bias, void* out, 
                     void* stream) {
   if (epilogue < 0 || epilogue > 3) return set_error(TASTE_E_ARG, "gemm: epilogue must be 0..3");
   return gemm_plain(a, w, bias, out, m, n, k, epilogue, static_cast<cudaStream_t>(stream));
+}
+
+int taste_encoder_set_mode(int mode) {
+  if (mode < 0 || mode > 2) return set_error(TASTE_E_ARG, "encoder_set_mode: mode must be 0, 1 or 2");
+  g_encoder_mode = mode;
+  return 0;
+}
+
+int taste_gemm_ex(const taste_gemm_ex_t* x, void* stream) {
+  if (!x) return set_error(TASTE_E_ARG, "gemm_ex: null descriptor");
+  if (x->epilogue < 0 || x->epilogue > 3) return set_error(TASTE_E_ARG, "gemm_ex: epilogue must be 0..3");
+  GemmDesc g;
+  g.a = x->a;
+  g.k_inner = x->k;
+  g.s_count = 1;
+  g.rows_in = x->m;
+  g.rows_out = x->m;
+  g.batches = 1;
+  g.s_stride = int64_t(x->k) * 2;
+  g.r_stride = int64_t(x->k) * 2;
+  g.b_stride = int64_t(x->m) * x->k * 2;
+  g.taps = 1;
+  g.w = x->w;
+  g.n = x->n;
+  g.bias = x->bias;
+  g.out = x->out;
+  g.ldc = x->n;
+  g.epilogue = x->epilogue;
+  g.ln_stats = x->ln_stats;
+  g.ln_nseg = x->ln_nseg;
+  g.ln_colsum = x->ln_colsum;
+  g.stats_out = x->stats_out;
+  g.out_bf16 = x->out_bf16;
+  return launch_gemm(g, static_cast<cudaStream_t>(stream));
 }
 
 int taste_attention_set_mode(int mode) {

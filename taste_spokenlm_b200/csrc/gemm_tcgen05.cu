@@ -32,6 +32,16 @@ struct GemmParams {
   void* out;
   int ldc;
   const float* pos;
+  // LayerNorm folding: a producer epilogue (LN == 2) also writes a bf16 copy of its fp32 output
+  // rows and, per row and 128-column segment, the partial (sum, sum of squares); a consumer epilogue (LN == 1) turns
+  // those into the row's mean / rstd and applies  rstd * (acc - mean * colsum[n]) + bias[n]  to the GEMM of the RAW
+  // bf16 rows against gamma-folded weights, which equals Linear(LayerNorm(row)).
+  const float* ln_stats;      // [rows][ln_nseg][2]
+  int ln_nseg;
+  float ln_inv_k;             // 1 / (128 * ln_nseg)
+  const float* ln_colsum;     // [n]
+  float* stats_out;           // [rows][n / 128][2]
+  __nv_bfloat16* out_bf16;    // [rows, ldc]
 };
 
 template <int BN>
@@ -108,9 +118,10 @@ TASTE_DEVINL void epilogue_chunk(const uint32_t (&acc)[32], const GemmParams& p,
 // columns go through a swizzled 4 KB smem tile so that every load / store instruction covers 4 rows x 128 contiguous
 // bytes instead of 32 rows x 16 bytes (thread-per-row).  The residual read-modify-write of out_proj / fc2 is what
 // bounds those GEMMs (K = 1280: 1.2 GB of HBM traffic against 0.3 TFLOP).
-template <int EPI>
+template <int EPI, int LN>
 TASTE_DEVINL void epilogue_chunk_f32_coalesced(const uint32_t (&acc)[32], const GemmParams& p, int64_t grow0,
-                                               int row0_in_batch, int n0, float4* scratch, int lane) {
+                                               int row0_in_batch, int n0, float4* scratch, int lane, float (&psum)[8],
+                                               float (&psq)[8]) {
   float v[32];
   if (p.bias != nullptr) {
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
@@ -161,17 +172,44 @@ TASTE_DEVINL void epilogue_chunk_f32_coalesced(const uint32_t (&acc)[32], const 
     if (EPI == EPI_RESID_F32 || EPI == EPI_GELU_POS_F32) {
       x.x += res[i].x; x.y += res[i].y; x.z += res[i].z; x.w += res[i].w;
     }
-    if (row0_in_batch + R < p.rows_out) *reinterpret_cast<float4*>(out_base + int64_t(R) * p.ldc) = x;
+    const bool row_ok = row0_in_batch + R < p.rows_out;
+    if (row_ok) *reinterpret_cast<float4*>(out_base + int64_t(R) * p.ldc) = x;
+    if (LN == 2) {
+      // bf16 copy of the new fp32 row (the next GEMM's A operand) and this lane's share of the row statistics
+      if (row_ok) {
+        uint2 u;
+        u.x = pack_bf16x2(x.x, x.y);
+        u.y = pack_bf16x2(x.z, x.w);
+        *reinterpret_cast<uint2*>(p.out_bf16 + (grow0 + R) * p.ldc + n0 + j * 4) = u;
+      }
+      psum[i] += (x.x + x.y) + (x.z + x.w);          // this lane's 4 columns; lanes are combined once per tile
+      psq[i] = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, psq[i]))));
+    }
   }
   __syncwarp();
 }
 
 // bf16 outputs, 64 columns (two TMEM chunks) at a time: bias (+ GELU) on the thread's own row, pack to bf16, then the
 // same swizzled 32 x 128-byte smem transpose so that stores cover 4 rows x 128 contiguous bytes per instruction.
-template <int EPI>
-TASTE_DEVINL void epilogue_pack_bf16(const uint32_t (&acc)[32], const GemmParams& p, int n0, uint32_t (&out16)[16]) {
+template <int EPI, int LN>
+TASTE_DEVINL void epilogue_pack_bf16(const uint32_t (&acc)[32], const GemmParams& p, int n0, uint32_t (&out16)[16],
+                                     float mu, float rstd) {
   float v[32];
-  if (p.bias != nullptr) {
+  if (LN == 1) {
+    // Linear(LayerNorm(row)) from the GEMM of the raw row against gamma-folded weights (p.bias holds b + W beta)
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+    const float4* c4 = reinterpret_cast<const float4*>(p.ln_colsum + n0);
+    const float nmr = -mu * rstd;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = __ldg(b4 + j);
+      const float4 c = __ldg(c4 + j);
+      v[4 * j + 0] = fmaf(__uint_as_float(acc[4 * j + 0]), rstd, fmaf(nmr, c.x, b.x));
+      v[4 * j + 1] = fmaf(__uint_as_float(acc[4 * j + 1]), rstd, fmaf(nmr, c.y, b.y));
+      v[4 * j + 2] = fmaf(__uint_as_float(acc[4 * j + 2]), rstd, fmaf(nmr, c.z, b.z));
+      v[4 * j + 3] = fmaf(__uint_as_float(acc[4 * j + 3]), rstd, fmaf(nmr, c.w, b.w));
+    }
+  } else if (p.bias != nullptr) {
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -379,7 +417,7 @@ struct Gemm2Cfg {
   static constexpr size_t kSmemBytes = 1024 + size_t(kStages) * kStageBytes + 256 + kScratchBytes;
 };
 
-template <int EPI>
+template <int EPI, int LN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
 gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                               const GemmParams p) {
@@ -517,14 +555,48 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const _
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN2 + half * (BN2 / 2));
       if (EPI == EPI_RESID_F32 || EPI == EPI_F32 || EPI == EPI_GELU_POS_F32) {
+        float psum[8], psq[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) psum[i] = psq[i] = 0.f;
 #pragma unroll 1
         for (int c = 0; c < BN2 / 64; ++c) {
           uint32_t acc[32];
           tmem_ld_32x32b_x32(taddr + uint32_t(c * 32), acc);
           tmem_ld_wait();
-          epilogue_chunk_f32_coalesced<EPI>(acc, p, grow0, row0_in_batch, nt * BN2 + half * (BN2 / 2) + c * 32, scratch, lane);
+          epilogue_chunk_f32_coalesced<EPI, LN>(acc, p, grow0, row0_in_batch, nt * BN2 + half * (BN2 / 2) + c * 32,
+                                                scratch, lane, psum, psq);
+        }
+        if (LN == 2) {
+          // this warp's 128 columns are one statistics segment of its 32 rows; the 8 lanes that share a row combine
+          // their partials with three shuffles, lane j == 0 writes the (sum, sum of squares) pair
+          const int seg = nt * (BN2 / 128) + half;
+          const int nseg = p.n_tiles * (BN2 / 128);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float s1 = psum[i], s2 = psq[i];
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+              s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+              s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            }
+            const int R = i * 4 + (lane >> 3);
+            if ((lane & 7) == 0 && row0_in_batch + R < p.rows_out)
+              *reinterpret_cast<float2*>(p.stats_out + ((grow0 + R) * nseg + seg) * 2) = make_float2(s1, s2);
+          }
         }
       } else {
+        float mu = 0.f, rstd = 0.f;
+        if (LN == 1 && valid) {
+          float s1 = 0.f, s2 = 0.f;
+          const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + grow * p.ln_nseg;
+          for (int sgm = 0; sgm < p.ln_nseg; ++sgm) {        // fixed order: deterministic
+            const float2 t = st[sgm];
+            s1 += t.x;
+            s2 += t.y;
+          }
+          mu = s1 * p.ln_inv_k;
+          rstd = rsqrtf(fmaxf(fmaf(-mu, mu, s2 * p.ln_inv_k), 0.f) + 1e-5f);
+        }
 #pragma unroll 1
         for (int c = 0; c < BN2 / 128; ++c) {        // 64 columns per step
           const int n0 = nt * BN2 + half * (BN2 / 2) + c * 64;
@@ -532,8 +604,8 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const _
           tmem_ld_32x32b_x32(taddr + uint32_t(c * 64), acc0);
           tmem_ld_32x32b_x32(taddr + uint32_t(c * 64 + 32), acc1);
           tmem_ld_wait();
-          epilogue_pack_bf16<EPI>(acc0, p, n0, lo);
-          epilogue_pack_bf16<EPI>(acc1, p, n0 + 32, hi);
+          epilogue_pack_bf16<EPI, LN>(acc0, p, n0, lo, mu, rstd);
+          epilogue_pack_bf16<EPI, LN>(acc1, p, n0 + 32, hi, mu, rstd);
           epilogue_store_bf16_coalesced(lo, hi, p, grow0, row0_in_batch, n0, scratch, lane);
         }
       }
@@ -603,9 +675,9 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
   return 0;
 }
 
-template <int EPI>
+template <int EPI, int LN>
 static int launch_cfg2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-  auto kern = gemm_bf16_tcgen05_2cta_kernel<EPI>;
+  auto kern = gemm_bf16_tcgen05_2cta_kernel<EPI, LN>;
   static int max_pairs = 0;
   if (max_pairs == 0) {
     TASTE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gemm2Cfg::kSmemBytes));
@@ -636,13 +708,23 @@ static int launch_cfg2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   return 0;
 }
 
-static int launch_epi2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int epi, cudaStream_t s) {
+static int launch_epi2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int epi, int ln, cudaStream_t s) {
+  if (ln == 1) {
+    if (epi == EPI_BF16) return launch_cfg2<EPI_BF16, 1>(ta, tb, p, s);
+    if (epi == EPI_GELU_BF16) return launch_cfg2<EPI_GELU_BF16, 1>(ta, tb, p, s);
+    return set_error(TASTE_E_ARG, "gemm: LayerNorm-in folding needs a bf16 epilogue");
+  }
+  if (ln == 2) {
+    if (epi == EPI_RESID_F32) return launch_cfg2<EPI_RESID_F32, 2>(ta, tb, p, s);
+    if (epi == EPI_GELU_POS_F32) return launch_cfg2<EPI_GELU_POS_F32, 2>(ta, tb, p, s);
+    return set_error(TASTE_E_ARG, "gemm: LayerNorm-out statistics need an fp32 epilogue");
+  }
   switch (epi) {
-    case EPI_BF16: return launch_cfg2<EPI_BF16>(ta, tb, p, s);
-    case EPI_GELU_BF16: return launch_cfg2<EPI_GELU_BF16>(ta, tb, p, s);
-    case EPI_RESID_F32: return launch_cfg2<EPI_RESID_F32>(ta, tb, p, s);
-    case EPI_F32: return launch_cfg2<EPI_F32>(ta, tb, p, s);
-    case EPI_GELU_POS_F32: return launch_cfg2<EPI_GELU_POS_F32>(ta, tb, p, s);
+    case EPI_BF16: return launch_cfg2<EPI_BF16, 0>(ta, tb, p, s);
+    case EPI_GELU_BF16: return launch_cfg2<EPI_GELU_BF16, 0>(ta, tb, p, s);
+    case EPI_RESID_F32: return launch_cfg2<EPI_RESID_F32, 0>(ta, tb, p, s);
+    case EPI_F32: return launch_cfg2<EPI_F32, 0>(ta, tb, p, s);
+    case EPI_GELU_POS_F32: return launch_cfg2<EPI_GELU_POS_F32, 0>(ta, tb, p, s);
   }
   return set_error(TASTE_E_ARG, "gemm: unknown epilogue %d", epi);
 }
@@ -675,7 +757,12 @@ int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
 
   // tile shape: CTA pairs (256 x 256) when there is at least one wave of pair tiles, else single-CTA 128 x {256,128}
   const int64_t pair_tiles = (d.n % 256 == 0) ? int64_t((d.rows_out + 2 * BM - 1) / (2 * BM)) * d.batches * (d.n / 256) : 0;
-  const bool use_pair = g_gemm_mode != 1 && pair_tiles >= num_sms() / 2;
+  const int ln = d.ln_stats ? 1 : (d.stats_out ? 2 : 0);
+  if (ln && (d.n % 256 != 0))
+    return set_error(TASTE_E_SHAPE, "gemm: LayerNorm folding needs N %% 256 == 0 (CTA-pair kernel)");
+  if (ln == 1 && (!d.ln_colsum || !d.bias || d.ln_nseg <= 0)) return set_error(TASTE_E_ARG, "gemm: LayerNorm-in folding needs stats, colsum and bias");
+  if (ln == 2 && !d.out_bf16) return set_error(TASTE_E_ARG, "gemm: LayerNorm-out needs the bf16 copy buffer");
+  const bool use_pair = ln != 0 || d.force_pair || (g_gemm_mode != 1 && pair_tiles >= num_sms() / 2);
   const int m_tiles = use_pair ? (d.rows_out + 2 * BM - 1) / (2 * BM) : (d.rows_out + BM - 1) / BM;
   const int64_t tiles256 = (d.n % 256 == 0) ? int64_t(m_tiles) * d.batches * (d.n / 256) : 0;
   const int bn = use_pair ? 128 /* B box: this CTA's half of the 256 columns */ : ((tiles256 >= num_sms()) ? 256 : 128);
@@ -717,7 +804,13 @@ int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
   p.out = d.out;
   p.ldc = d.ldc;
   p.pos = d.pos;
-  if (use_pair) return launch_epi2(ta, tb, p, d.epilogue, stream);
+  p.ln_stats = d.ln_stats;
+  p.ln_nseg = d.ln_nseg;
+  p.ln_inv_k = d.ln_nseg > 0 ? 1.0f / float(128 * d.ln_nseg) : 0.f;
+  p.ln_colsum = d.ln_colsum;
+  p.stats_out = d.stats_out;
+  p.out_bf16 = static_cast<__nv_bfloat16*>(d.out_bf16);
+  if (use_pair) return launch_epi2(ta, tb, p, d.epilogue, ln, stream);
   return bn == 256 ? launch_epi<256>(ta, tb, p, d.epilogue, stream) : launch_epi<128>(ta, tb, p, d.epilogue, stream);
 }
 

@@ -61,6 +61,13 @@ struct GemmDesc {
   int ldc = 0;
   int epilogue = EPI_BF16;
   const float* pos = nullptr;
+  // LayerNorm folding (CTA-pair kernel only; see GemmParams in gemm_tcgen05.cu)
+  const float* ln_stats = nullptr;    // consumer: [rows][ln_nseg][2]; requires ln_colsum and bias (= b + W beta)
+  int ln_nseg = 0;
+  const float* ln_colsum = nullptr;
+  float* stats_out = nullptr;         // producer: [rows][n/128][2]; requires out_bf16
+  void* out_bf16 = nullptr;
+  bool force_pair = false;
 };
 int launch_gemm(const GemmDesc& d, cudaStream_t stream);
 void set_gemm_mode(int mode);

@@ -131,7 +131,9 @@ class TowerEngine(FrontendEngine):
             wk = sd[p + "k_proj.weight"].detach().to(dev, torch.float32)                  # no bias, CW:315
             wv = sd[p + "v_proj.weight"].detach().to(dev, torch.float32)
             bv = sd[p + "v_proj.bias"].detach().to(dev, torch.float32)
-            return (b16(prefix + "wqkv", torch.cat([wq, wk, wv], 0)),
+            wcat = torch.cat([wq, wk, wv], 0)
+            self._keep[prefix + "wqkv_f32"] = wcat          # transient: consumed by the LayerNorm fold (encoder layers)
+            return (b16(prefix + "wqkv", wcat),
                     f32(prefix + "bqkv", torch.cat([bq, torch.zeros_like(bq), bv], 0)))
 
         w = _lib.Weights()
@@ -162,6 +164,12 @@ class TowerEngine(FrontendEngine):
             L.b1 = f32(k + "b1", sd[p + "fc1.bias"])
             L.w2 = b16(k + "w2", sd[p + "fc2.weight"])
             L.b2 = f32(k + "b2", sd[p + "fc2.bias"])
+            # LayerNorm-folded copies (taste_enc_layer_t): W' = W * gamma (bf16), c = rowsum(W'), b' = b + W beta
+            self._fold_ln(L, k, "qkv", self._keep[k + "wqkv_f32"], self._keep[k + "bqkv"],
+                          sd[p + "self_attn_layer_norm.weight"], sd[p + "self_attn_layer_norm.bias"])
+            del self._keep[k + "wqkv_f32"]
+            self._fold_ln(L, k, "1", sd[p + "fc1.weight"].detach().to(dev, torch.float32), self._keep[k + "b1"],
+                          sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"])
         w.enc = C.cast(enc, C.c_void_p)
         w.enc_ln_w = f32("enc_ln_w", sd[ENC + "layer_norm.weight"])
         w.enc_ln_b = f32("enc_ln_b", sd[ENC + "layer_norm.bias"])
@@ -174,6 +182,7 @@ class TowerEngine(FrontendEngine):
             L.ln1_w = f32(k + "ln1_w", sd[p + "self_attn_layer_norm.weight"])
             L.ln1_b = f32(k + "ln1_b", sd[p + "self_attn_layer_norm.bias"])
             L.wqkv, L.bqkv = qkv(k, p + "self_attn.")
+            self._keep.pop(k + "wqkv_f32", None)
             L.wo = b16(k + "wo", sd[p + "self_attn.out_proj.weight"])
             L.bo = f32(k + "bo", sd[p + "self_attn.out_proj.bias"])
             L.lnx_w = f32(k + "lnx_w", sd[p + "encoder_attn_layer_norm.weight"])
@@ -199,6 +208,19 @@ class TowerEngine(FrontendEngine):
         self.w = w
         self._enc_arr, self._dec_arr = enc, dec
         _lib.check(self.lib.taste_handle_create(C.byref(w), C.byref(self.handle)), "taste_handle_create")
+
+    def _fold_ln(self, L, key, which, w_f32, b_f32, gamma, beta):
+        """Fill the `*_ln` fields of an encoder layer: Linear(LayerNorm(x)) = rstd * (x W'^T - mean * c) + b'."""
+        dev = self.device
+        g = gamma.detach().to(dev, torch.float32)
+        bt = beta.detach().to(dev, torch.float32)
+        wf = (w_f32 * g[None, :]).to(torch.bfloat16)
+        c = wf.float().sum(dim=1)                      # from the bf16-rounded W': what the tensor core multiplies
+        bp = b_f32 + w_f32 @ bt
+        names = ("wqkv_ln", "bqkv_ln", "cqkv_ln") if which == "qkv" else ("w1_ln", "b1_ln", "c1_ln")
+        setattr(L, names[0], self._dev(key + names[0], wf))
+        setattr(L, names[1], self._dev(key + names[1], bp))
+        setattr(L, names[2], self._dev(key + names[2], c))
 
     def _pack_rvq(self, w, sd):
         cfg, dev = self.cfg, self.device

@@ -77,6 +77,49 @@ def test_gemm(lib, m, n, k, epi, mode):
     assert _rel(out.float(), ref) < tol
 
 
+@pytest.mark.parametrize("m,d,n", [(2048, 1280, 3840), (3000, 256, 512), (5000, 1280, 5120)])
+@pytest.mark.parametrize("gelu", [0, 1])
+def test_gemm_layernorm_folding(lib, m, d, n, gelu):
+    """Producer GEMM (residual epilogue) emits h, bf16(h) and per-128-column row statistics; consumer GEMM on the RAW
+    bf16 rows with gamma-folded weights reproduces Linear(LayerNorm(h)) (include/taste_b200.h: taste_gemm_ex)."""
+    torch.manual_seed(m + d + n + gelu)
+    kk = 256
+    a = (torch.randn(m, kk, device="cuda") * 0.5).bfloat16()
+    wo = (torch.randn(d, kk, device="cuda") / math.sqrt(kk)).bfloat16()
+    bo = torch.randn(d, device="cuda") * 0.1
+    h0 = torch.randn(m, d, device="cuda") * 2.0 + 0.3
+    h = h0.clone()
+    hb = torch.full((m, d), float("nan"), device="cuda").bfloat16()
+    stats = torch.full((m, d // 128, 2), float("nan"), device="cuda")
+    g = _lib.GemmEx(a=a.data_ptr(), w=wo.data_ptr(), bias=bo.data_ptr(), out=h.data_ptr(), m=m, n=d, k=kk, epilogue=2,
+                    stats_out=stats.data_ptr(), out_bf16=hb.data_ptr())
+    _lib.check(lib.taste_gemm_ex(C.byref(g), _stream()), "gemm_ex producer")
+    torch.cuda.synchronize()
+    h_ref = h0 + a.float() @ wo.float().T + bo
+    assert _rel(h, h_ref) < 1e-5
+    assert torch.equal(hb, h.bfloat16())
+    seg = h.view(m, d // 128, 128)
+    assert _rel(stats[..., 0], seg.sum(-1)) < 1e-5 and _rel(stats[..., 1], (seg * seg).sum(-1)) < 1e-5
+    # consumer
+    gamma = 1.0 + 0.2 * torch.randn(d, device="cuda")
+    beta = 0.1 * torch.randn(d, device="cuda")
+    w = torch.randn(n, d, device="cuda") / math.sqrt(d)
+    b = torch.randn(n, device="cuda") * 0.1
+    wf = (w * gamma[None, :]).bfloat16()
+    colsum = wf.float().sum(1)
+    bp = b + w @ beta
+    out = torch.full((m, n), float("nan"), device="cuda").bfloat16()
+    g2 = _lib.GemmEx(a=hb.data_ptr(), w=wf.data_ptr(), bias=bp.data_ptr(), out=out.data_ptr(), m=m, n=n, k=d,
+                     epilogue=gelu, ln_stats=stats.data_ptr(), ln_nseg=d // 128, ln_colsum=colsum.data_ptr())
+    _lib.check(lib.taste_gemm_ex(C.byref(g2), _stream()), "gemm_ex consumer")
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(h.double(), (d,), gamma.double(), beta.double(), 1e-5) @ w.double().T + b.double()
+    if gelu:
+        ref = torch.nn.functional.gelu(ref)
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out.float(), ref) < 6e-3          # bf16 A / W' / output rounding, same budget as LayerNorm -> bf16 -> GEMM
+
+
 def test_gemm_rejects_bad_shapes(lib):
     a = torch.zeros(128, 96, device="cuda").bfloat16()
     w = torch.zeros(128, 96, device="cuda").bfloat16()
