@@ -234,51 +234,43 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
         mbar_wait(&s_full[i], uint32_t(g & 1));
         FA_TRACE(i, g * 8 + 1);
         tc_fence_after();
-        // The S tile is read twice from TMEM in 32-column chunks (pass 1: row maximum, pass 2: exponentials).
-        // tcgen05.wait::ld waits for every load in flight, so the loads are grouped to expose the TMEM latency only
-        // about three times per block: {c0,c1,c2} -> one wait; {c3, c0 again} under the maxima of c1,c2 -> one wait;
-        // pass 2 then always has the next chunk in flight while it exponentiates the current one.
-        // (Tried and rejected, with measurements in DESIGN.md: a speculative single pass against the stale maximum — on
-        // high-variance scores a warp redoes most early blocks; and 16 softmax warps with two threads per row exchanging
-        // maxima through smem — 1.45 ms against 1.17 ms for this layout.)
+        // The whole S row (128 fp32) is read into registers ONCE: one exposed TMEM latency per block, and the S tile
+        // can be handed back to the MMA warp immediately, so the next block's QK^T runs under this block's entire
+        // softmax.  P goes back to TMEM in four 16-column stores as soon as each 32-score chunk is exponentiated,
+        // which keeps the live set at 128 scores + 16 packed probabilities.
+        // (Tried and rejected, with measurements in DESIGN.md: two passes over TMEM with 64 live scores; a speculative
+        // single pass against the stale maximum; 16 softmax warps with two threads per row.)
         const int valid = p.kv_len - j * FA_BK;       // keys of this block that exist
-        uint32_t ra[32], rb[32], pk[32];              // pk: third load buffer in pass 1, packed probabilities in pass 2
-        tmem_ld_32x32b_x32(t_s, ra);
-        tmem_ld_32x32b_x32(t_s + 32, rb);
+        uint32_t r[4][32];
+        tmem_ld_32x32b_x32(t_s, r[0]);
+        tmem_ld_32x32b_x32(t_s + 32, r[1]);
         if (pending) {
-          // P of the previous block: its stores (sourced from pk) are waited for only now, under the latency of the
-          // loads above, and before pk is reused as a load destination
+          // P of the previous block: its stores are waited for only now, under the latency of the loads above
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&p_full[i]);
           pending = false;
         }
-        tmem_ld_32x32b_x32(t_s + 64, pk);
+        tmem_ld_32x32b_x32(t_s + 64, r[2]);
+        tmem_ld_32x32b_x32(t_s + 96, r[3]);
         tmem_ld_wait();
-        auto mask_chunk = [&](uint32_t (&x)[32], int c) {
-          if (valid < FA_BK) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[i]);       // every read of S has landed: the next QK^T may overwrite it
+        FA_TRACE(i, g * 8 + 3);
+        if (valid < FA_BK) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
 #pragma unroll
             for (int e = 0; e < 32; ++e)
-              if (c * 32 + e >= valid) x[e] = 0xff800000u;      // -inf
-          }
-        };
+              if (c * 32 + e >= valid) r[c][e] = 0xff800000u;      // -inf
+        }
         float mx = -INFINITY;
-        mask_chunk(ra, 0);
 #pragma unroll
-        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(ra[e]));
-        tmem_ld_32x32b_x32(t_s + 96, ra);              // c3
-        mask_chunk(rb, 1);
+        for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(rb[e]));
-        tmem_ld_32x32b_x32(t_s, rb);                   // c0 again, for pass 2
-        mask_chunk(pk, 2);
-#pragma unroll
-        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(pk[e]));
-        tmem_ld_wait();
-        mask_chunk(ra, 3);
-#pragma unroll
-        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(ra[e]));
+          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(r[c][e]));
         FA_TRACE(i, g * 8 + 2);
         const bool grow = mx > m_used + 5.545177f;     // 8 in log2 units; first block: m_used = -inf
         const bool any_grow = __any_sync(0xffffffffu, grow);
@@ -289,30 +281,18 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
           l_run *= alpha;
           m_used = m_new;
         }
-        // pass 2: p = exp2(s * log2e - m * log2e), row sum, bf16 P back to TMEM.  Chunk c lives in rb (c even) / ra (c odd)
         const float neg_m = -m_used * kLog2e;
         const uint64_t negm2 = f2_pack(neg_m, neg_m);
         const uint64_t log2e2 = f2_pack(kLog2e, kLog2e);
         uint64_t sum2 = f2_pack(0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          uint32_t (&cur)[32] = (c & 1) ? ra : rb;
-          uint32_t (&nxt)[32] = (c & 1) ? rb : ra;
-          if (c > 0) tmem_ld_wait();
-          if (c < 3) {
-            tmem_ld_32x32b_x32(t_s + uint32_t((c + 1) * 32), nxt);
-          } else {                                     // every read of S has landed: the next QK^T may overwrite it
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_free[i]);
-            FA_TRACE(i, g * 8 + 3);
-          }
-          mask_chunk(cur, c);
+          uint32_t pk[16];
           // Exponentials in pairs (packed FFMA2 / FADD2).  16/clk/SM of MUFU.EX2 would cap the tensor pipe at 50 %,
           // so POLY of every 16 pairs are evaluated on the FMA pipe instead (exp2_poly2).
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            const uint64_t t2 = f2_fma(f2_pack(__uint_as_float(cur[2 * e]), __uint_as_float(cur[2 * e + 1])), log2e2, negm2);
+            const uint64_t t2 = f2_fma(f2_pack(__uint_as_float(r[c][2 * e]), __uint_as_float(r[c][2 * e + 1])), log2e2, negm2);
             float p0, p1;
             if (((e * POLY) & 15) < POLY && POLY > 0) {       // evenly spread POLY of 16
               exp2_poly2(t2, p0, p1);
@@ -322,9 +302,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
               p1 = fast_exp2(p1);
             }
             sum2 = f2_add(sum2, f2_pack(p0, p1));
-            pk[(c & 1) * 16 + e] = pack_bf16x2(p0, p1);
+            pk[e] = pack_bf16x2(p0, p1);
           }
-          if (c == 1 && j > 0) {
+          if (c == 0 && j > 0) {
             // Only now is the previous block's P V needed: P_i has been consumed (it may be overwritten) and O_i is
             // stable (it may be rescaled).  On the first block of an item the output pass below already waited.
             FA_TRACE(i, g * 8 + 4);
@@ -332,19 +312,25 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
             FA_TRACE(i, g * 8 + 5);
             tc_fence_after();
             if (any_grow) {
-              tmem_ld_wait();                          // drain the in-flight S chunk before reusing the wait below
 #pragma unroll
-              for (int cc = 0; cc < FA_HD / 32; ++cc) {
-                uint32_t o[32];
-                tmem_ld_32x32b_x32(t_o + uint32_t(cc * 32), o);
+              for (int cc = 0; cc < FA_HD / 16; ++cc) {
+                uint32_t o[16];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
+                    "%13, %14, %15}, [%16];"
+                    : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]),
+                      "=r"(o[8]), "=r"(o[9]), "=r"(o[10]), "=r"(o[11]), "=r"(o[12]), "=r"(o[13]), "=r"(o[14]),
+                      "=r"(o[15])
+                    : "r"(t_o + uint32_t(cc * 16))
+                    : "memory");
                 tmem_ld_wait();
 #pragma unroll
-                for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-                tmem_st_32x32b_x32(t_o + uint32_t(cc * 32), o);
+                for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+                tmem_st_32x32b_x16(t_o + uint32_t(cc * 16), o);
               }
             }
           }
-          if (c & 1) tmem_st_32x32b_x32(t_p + uint32_t((c >> 1) * 32), pk);
+          tmem_st_32x32b_x16(t_p + uint32_t(c * 16), pk);
         }
         float sum0, sum1;
         f2_unpack(sum2, sum0, sum1);
