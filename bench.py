@@ -331,6 +331,21 @@ def main():
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps,
                "api": "WhisperFrontendB200.forward_device + TasteAudioTowerB200.forward (pinned host in, host indices out)"}
 
+    # ---- single-utterance latency (BASELINE config 5's tokenizer call: B = 1, 30 s window, same T) ------------------
+    lat_ms = None
+    if rank == 0 and not args.no_e2e:
+        one = {k: (v[:1].contiguous() if torch.is_tensor(v) else v[:1]) for k, v in batch.items()}
+        for _ in range(3):
+            eng.tokenize_device(one["wav"], one["n_samples"], one["ids"], one["wid"], one["lengths_host"])
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(10):
+            eng.tokenize_device(one["wav"], one["n_samples"], one["ids"], one["wid"], one["lengths_host"])
+        g1.record()
+        torch.cuda.synchronize()
+        lat_ms = g0.elapsed_time(g1) / 10
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -390,6 +405,7 @@ def main():
         "tflops_per_gpu": flops_per_utt * (value / UTT_SECONDS / world) / 1e12,
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "stages": stages,
         "cpu_baseline": cpu_baseline,
+        "latency_b1_ms": lat_ms,
     }
     if args.layers != 32:
         line["INVALID"] = "debug run with a reduced layer count; not the named config"
