@@ -27,7 +27,7 @@ constexpr int FA_HD = 64;
 constexpr int FA_STAGES = 4;
 constexpr int FA_THREADS = 352;
 #ifndef FA_POLY
-#define FA_POLY 4                   // of every 16 score pairs, this many take the polynomial exp2 path
+#define FA_POLY 6                   // of every 16 score pairs, this many take the polynomial exp2 path
 #endif
 constexpr uint32_t FA_TILE_BYTES = FA_BQ * FA_HD * 2;      // 16 KB: one Q, K or V tile
 // Q is double buffered (2 x 2 tiles) so the next work item's queries load under the current item's last blocks
@@ -270,7 +270,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
-          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(r[c][e]));
+          for (int e = 0; e < 32; ++e)
+            mx = fmaxf(mx, __uint_as_float(r[c][e]));
         FA_TRACE(i, g * 8 + 2);
         const bool grow = mx > m_used + 5.545177f;     // 8 in log2 units; first block: m_used = -inf
         const bool any_grow = __any_sync(0xffffffffu, grow);
@@ -434,7 +435,7 @@ int launch_attention_tcgen05(const AttnDesc& d, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
 #define FA_CFG(V, P) TASTE_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<V, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM))
-    FA_CFG(0, FA_POLY); FA_CFG(4, FA_POLY); FA_CFG(0, 0); FA_CFG(0, 7); FA_CFG(0, 10);
+    FA_CFG(0, FA_POLY); FA_CFG(4, FA_POLY); FA_CFG(0, 0);
 #undef FA_CFG
     configured = true;
   }
@@ -460,12 +461,9 @@ int launch_attention_tcgen05(const AttnDesc& d, cudaStream_t stream) {
   const double pairs = double(d.batch) * d.q_len * d.kv_len;
   ProfScope ps(stream, d.kclass == KC_ATTN_ENC ? KC_ATTN_ENC : KC_ATTN_TC, 4.0 * pairs * FA_HD * d.heads,
                2.0 * FA_HD * d.heads * double(d.batch) * (2.0 * d.q_len + 2.0 * d.kv_len));
-  const char* ep = getenv("TASTE_FA_POLY");          // experiment knob: 0 / 7 / 10 of every 16 pairs on the FMA pipe
-  const int poly = ep ? atoi(ep) : FA_POLY;
+  const char* ep = getenv("TASTE_FA_POLY");          // A/B knob: "0" = every exponential on the MUFU
   if (var == 4) attention_tcgen05_kernel<4, FA_POLY><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
-  else if (poly == 0) attention_tcgen05_kernel<0, 0><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
-  else if (poly == 7) attention_tcgen05_kernel<0, 7><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
-  else if (poly == 10) attention_tcgen05_kernel<0, 10><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
+  else if (ep && atoi(ep) == 0) attention_tcgen05_kernel<0, 0><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
   else attention_tcgen05_kernel<0, FA_POLY><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
   TASTE_CUDA_OK(cudaGetLastError());
   return 0;

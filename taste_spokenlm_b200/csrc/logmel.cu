@@ -3,7 +3,7 @@
 //   400-point real DFT, folded over the n <-> 400-n symmetry so only 199 x 201 twiddle products are needed per
 //   frame -> |X|^2 -> sparse Slaney mel projection (394 non-zeros) -> log10(clamp 1e-10) -> per-utterance max.
 // A second small kernel applies the `max - 8` floor and the (x+4)/4 scaling and emits fp32 and/or bf16 features.
-// Arithmetic is fp32 FFMA throughout: the 80 dB dynamic range kept by the `max - 8` floor rules out a single
+// Arithmetic is fp32 (packed FFMA2) throughout: the 80 dB dynamic range kept by the `max - 8` floor rules out a single
 // bf16 tensor-core pass (SURVEY §7 hard part 6).
 #include "common.cuh"
 #include "internal.h"
@@ -12,10 +12,10 @@ namespace taste {
 
 constexpr int LM_FRAMES = 64;          // frames per CTA
 constexpr int LM_THREADS = 256;        // 8 frame groups x 32 bin lanes
-constexpr int LM_FPT = 8;              // frames per thread
-constexpr int LM_KPT = 7;              // bins per thread: k = lane + 32*j  (224 >= 201)
+constexpr int LM_FPT = 8;              // frames per thread (4 packed pairs)
+constexpr int LM_KPT = 4;              // half-spectrum bins per thread: k' = lane + 32*j  (128 >= 101)
 constexpr int LM_NH = 199;             // folded terms n = 1..199
-constexpr int LM_LDF = 65;             // padded frame stride of the folded arrays (bank-conflict free both ways)
+constexpr int LM_LDF = 66;             // padded frame stride of the folded arrays (even: 8-byte aligned frame pairs)
 constexpr int LM_LDP = 209;            // padded bin stride of the power tile
 constexpr int LM_SMEM = (2 * 200 * LM_LDF + LM_FRAMES) * 4;   // E, O, y200
 
@@ -36,14 +36,21 @@ __device__ __forceinline__ float ordered_to_float(unsigned int k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
 }
 
+// The 400-point real DFT of a windowed frame y uses two symmetries:
+//   n <-> 400-n :  Re X[k] = y[0] + (-1)^k y[200] + sum_{n=1..199} E[n] cos(2 pi k n / 400),  E[n] = y[n] + y[400-n]
+//                  Im X[k] =                      - sum_{n=1..199} O[n] sin(2 pi k n / 400),  O[n] = y[n] - y[400-n]
+//   k <-> 200-k :  cos(2 pi (200-k) n / 400) = (-1)^n cos(2 pi k n / 400),  sin(...) = -(-1)^n sin(2 pi k n / 400)
+// so with the sums split by the parity of n (Ce/Co over E, Se/So over O) only k' = 0..100 is accumulated:
+//   Re X[k'] = Ce + Co + s,  Re X[200-k'] = Ce - Co + s,  |Im X[k']| = |Se + So|,  |Im X[200-k']| = |Se - So|.
+// That is a quarter of the multiply-adds of the plain 400 x 201 DFT; they run as packed FFMA2 over frame pairs.
 __global__ void __launch_bounds__(LM_THREADS, 1)
 logmel_tile_kernel(const float* __restrict__ wav, const int32_t* __restrict__ n_samples, int64_t wav_stride,
                    const float* __restrict__ dft_cos, const float* __restrict__ dft_sin, const float* __restrict__ hann,
                    const int32_t* __restrict__ mel_start, const int32_t* __restrict__ mel_count,
                    const float* __restrict__ mel_weight, float* __restrict__ logspec, unsigned int* __restrict__ umax) {
-  extern __shared__ float lm_smem[];
-  float* sE = lm_smem;                       // [200][65]  w[n] * (x[n] + x[400-n]),  row n-1
-  float* sO = sE + 200 * LM_LDF;             // [200][65]  w[n] * (x[n] - x[400-n])
+  extern __shared__ __align__(16) float lm_smem[];
+  float* sE = lm_smem;                       // [200][66]  w[n] * (x[n] + x[400-n]),  row n-1
+  float* sO = sE + 200 * LM_LDF;             // [200][66]  w[n] * (x[n] - x[400-n])
   float* sY200 = sO + 200 * LM_LDF;          // [64]
   float* sP = lm_smem;                       // aliases sE/sO after the DFT: [64][209]
   __shared__ float s_red[LM_THREADS / 32];
@@ -74,34 +81,42 @@ logmel_tile_kernel(const float* __restrict__ wav, const int32_t* __restrict__ n_
   }
   __syncthreads();
 
-  // ---- stage 2: DFT as a register-tiled fp32 product against the twiddle tables ----
+  // ---- stage 2: half-spectrum DFT, register tile of 8 frames (4 packed pairs) x 4 bins x {Ce, Co, Se, So} ----
   const int fg = tid >> 5;                    // frame group: frames fg*8 .. fg*8+7
   const int lane = tid & 31;
-  float re[LM_FPT][LM_KPT], im[LM_FPT][LM_KPT];
+  uint64_t ce[LM_FPT / 2][LM_KPT], co[LM_FPT / 2][LM_KPT], se[LM_FPT / 2][LM_KPT], so[LM_FPT / 2][LM_KPT];
 #pragma unroll
-  for (int i = 0; i < LM_FPT; ++i)
+  for (int i = 0; i < LM_FPT / 2; ++i)
 #pragma unroll
-    for (int j = 0; j < LM_KPT; ++j) re[i][j] = im[i][j] = 0.f;
+    for (int j = 0; j < LM_KPT; ++j) ce[i][j] = co[i][j] = se[i][j] = so[i][j] = f2_pack(0.f, 0.f);
 
-#pragma unroll 2
-  for (int n = 0; n < LM_NH; ++n) {
-    float c[LM_KPT], s[LM_KPT];
+  auto accumulate = [&](int row, uint64_t (&accc)[LM_FPT / 2][LM_KPT], uint64_t (&accs)[LM_FPT / 2][LM_KPT]) {
+    float c[LM_KPT], sn[LM_KPT];
 #pragma unroll
     for (int j = 0; j < LM_KPT; ++j) {
-      c[j] = __ldg(dft_cos + n * TASTE_DFT_LD + lane + 32 * j);
-      s[j] = __ldg(dft_sin + n * TASTE_DFT_LD + lane + 32 * j);
+      c[j] = __ldg(dft_cos + row * TASTE_DFT_LD + lane + 32 * j);
+      sn[j] = __ldg(dft_sin + row * TASTE_DFT_LD + lane + 32 * j);
     }
+    const uint64_t* e2 = reinterpret_cast<const uint64_t*>(sE + row * LM_LDF + fg * LM_FPT);
+    const uint64_t* o2 = reinterpret_cast<const uint64_t*>(sO + row * LM_LDF + fg * LM_FPT);
 #pragma unroll
-    for (int i = 0; i < LM_FPT; ++i) {
-      const float e = sE[n * LM_LDF + fg * LM_FPT + i];
-      const float o = sO[n * LM_LDF + fg * LM_FPT + i];
+    for (int i = 0; i < LM_FPT / 2; ++i) {
+      const uint64_t e = e2[i];               // frames (2i, 2i+1) of this group: warp-wide broadcast
+      const uint64_t o = o2[i];
 #pragma unroll
       for (int j = 0; j < LM_KPT; ++j) {
-        re[i][j] = fmaf(e, c[j], re[i][j]);
-        im[i][j] = fmaf(o, s[j], im[i][j]);
+        accc[i][j] = f2_fma(e, f2_pack(c[j], c[j]), accc[i][j]);
+        accs[i][j] = f2_fma(o, f2_pack(sn[j], sn[j]), accs[i][j]);
       }
     }
+  };
+#pragma unroll 3
+  for (int row = 0; row < LM_NH - 1; row += 2) {      // n = row + 1: odd first, then even (99 iterations = 3 x 33)
+    accumulate(row, co, so);
+    accumulate(row + 1, ce, se);
   }
+  accumulate(LM_NH - 1, co, so);                      // n = 199 (odd)
+
   float y200[LM_FPT];
 #pragma unroll
   for (int i = 0; i < LM_FPT; ++i) y200[i] = sY200[fg * LM_FPT + i];
@@ -109,12 +124,24 @@ logmel_tile_kernel(const float* __restrict__ wav, const int32_t* __restrict__ n_
 #pragma unroll
   for (int j = 0; j < LM_KPT; ++j) {
     const int k = lane + 32 * j;
-    if (k <= 200) {
-      const float sgn = (k & 1) ? -1.f : 1.f;          // y[0] = 0 (periodic Hann), y[200] * (-1)^k
+    if (k <= 100) {
+      const float sgn = (k & 1) ? -1.f : 1.f;          // y[0] = 0 (periodic Hann); y[200] enters with (-1)^k
 #pragma unroll
-      for (int i = 0; i < LM_FPT; ++i) {
-        const float r = re[i][j] + sgn * y200[i];
-        sP[(fg * LM_FPT + i) * LM_LDP + k] = r * r + im[i][j] * im[i][j];
+      for (int i = 0; i < LM_FPT / 2; ++i) {
+        float cev[2], cov[2], sev[2], sov[2];
+        f2_unpack(ce[i][j], cev[0], cev[1]);
+        f2_unpack(co[i][j], cov[0], cov[1]);
+        f2_unpack(se[i][j], sev[0], sev[1]);
+        f2_unpack(so[i][j], sov[0], sov[1]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int f = fg * LM_FPT + 2 * i + h;
+          const float s = sgn * y200[2 * i + h];
+          const float re_lo = (cev[h] + cov[h]) + s, im_lo = sev[h] + sov[h];
+          const float re_hi = (cev[h] - cov[h]) + s, im_hi = sev[h] - sov[h];
+          sP[f * LM_LDP + k] = re_lo * re_lo + im_lo * im_lo;
+          if (k < 100) sP[f * LM_LDP + 200 - k] = re_hi * re_hi + im_hi * im_hi;
+        }
       }
     }
   }
@@ -190,7 +217,7 @@ int launch_logmel(const taste_weights_t& w, const float* wav, const int32_t* n_s
   // algorithmic bytes of the whole front-end: waveform in + features out (3.456 MB per utterance),
   // booked on the tile kernel; the finish pass is booked with its own read+write
   const double feat_elems = double(batch) * TASTE_N_FRAMES * TASTE_N_MELS;
-  ProfScope ps1(stream, KC_LOGMEL_TILE, double(batch) * TASTE_N_FRAMES * (2.0 * 2 * 199 * 201 + 2.0 * 394),
+  ProfScope ps1(stream, KC_LOGMEL_TILE, double(batch) * TASTE_N_FRAMES * (2.0 * 2 * 199 * 101 + 2.0 * 394),
                 double(batch) * TASTE_N_SAMPLES * 4.0 + feat_elems * 4.0);
   logmel_tile_kernel<<<grid, LM_THREADS, LM_SMEM, stream>>>(wav, n_samples, wav_stride, w.dft_cos, w.dft_sin, w.hann,
                                                             w.mel_start, w.mel_count, w.mel_weight, logspec, scratch_max);

@@ -24,8 +24,8 @@ rvq_encode_kernel(const float* __restrict__ z, const int32_t* __restrict__ lengt
                   const float* __restrict__ code_t, const float* __restrict__ code, const float* __restrict__ code_sq,
                   const float* __restrict__ wout_t, const float* __restrict__ bout, int64_t* __restrict__ indices,
                   float* __restrict__ quantized) {
-  __shared__ float s_res[RVQ_ROWS][RVQ_DC];       // residual
-  __shared__ float s_acc[RVQ_ROWS][RVQ_DC];       // sum of selected codes
+  __shared__ __align__(16) float s_res[RVQ_ROWS][RVQ_DC];       // residual
+  __shared__ __align__(16) float s_acc[RVQ_ROWS][RVQ_DC];       // sum of selected codes
   float (*s_in)[RVQ_DC] = s_acc;                  // input staging chunk; dead before s_acc is first used
   __shared__ float s_x2[RVQ_ROWS];
   __shared__ float s_bd[RVQ_THREADS / 32][RVQ_ROWS];
@@ -64,12 +64,19 @@ rvq_encode_kernel(const float* __restrict__ z, const int32_t* __restrict__ lengt
         s_in[r][c] = (row0 + r < n_rows && k0 + c < in_dim) ? z[int64_t(row0 + r) * in_dim + k0 + c] : 0.f;
       }
       __syncthreads();
-      const int kmax = min(RVQ_DC, in_dim - k0);
-#pragma unroll 4
-      for (int k = 0; k < kmax; ++k) {
-        const float wv = __ldg(win_t + int64_t(k0 + k) * RVQ_DC + tid);
+      // four k at a time: one 16-byte broadcast read of the staged row per 4 multiply-adds (the loop is LDS-bound)
+      const int kmax = min(RVQ_DC, in_dim - k0);           // in_dim is a multiple of 4 (checked by the launcher)
+#pragma unroll 2
+      for (int k = 0; k < kmax; k += 4) {
+        const float w0 = __ldg(win_t + int64_t(k0 + k + 0) * RVQ_DC + tid);
+        const float w1 = __ldg(win_t + int64_t(k0 + k + 1) * RVQ_DC + tid);
+        const float w2 = __ldg(win_t + int64_t(k0 + k + 2) * RVQ_DC + tid);
+        const float w3 = __ldg(win_t + int64_t(k0 + k + 3) * RVQ_DC + tid);
 #pragma unroll
-        for (int r = 0; r < RVQ_ROWS; ++r) acc[r] = fmaf(s_in[r][k], wv, acc[r]);
+        for (int r = 0; r < RVQ_ROWS; ++r) {
+          const float4 x = *reinterpret_cast<const float4*>(&s_in[r][k]);
+          acc[r] = fmaf(x.w, w3, fmaf(x.z, w2, fmaf(x.y, w1, fmaf(x.x, w0, acc[r]))));
+        }
       }
     }
     const float bv = __ldg(bin + tid);
@@ -94,15 +101,20 @@ rvq_encode_kernel(const float* __restrict__ z, const int32_t* __restrict__ lengt
 #pragma unroll
     for (int r = 0; r < RVQ_ROWS; ++r) d0[r] = d1[r] = 0.f;
     const float* ct = code_t + int64_t(q) * RVQ_DC * RVQ_K;
-#pragma unroll 2
-    for (int c = 0; c < RVQ_DC; ++c) {
-      const float e0 = __ldg(ct + c * RVQ_K + tid);
-      const float e1 = __ldg(ct + c * RVQ_K + tid + RVQ_THREADS);
+#pragma unroll 1
+    for (int c = 0; c < RVQ_DC; c += 4) {
+      float e0[4], e1[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        e0[u] = __ldg(ct + (c + u) * RVQ_K + tid);
+        e1[u] = __ldg(ct + (c + u) * RVQ_K + tid + RVQ_THREADS);
+      }
 #pragma unroll
       for (int r = 0; r < RVQ_ROWS; ++r) {
-        const float rv = s_res[r][c];
-        d0[r] = fmaf(rv, e0, d0[r]);
-        d1[r] = fmaf(rv, e1, d1[r]);
+        const float4 rv = *reinterpret_cast<const float4*>(&s_res[r][c]);
+        // same summation order as one element at a time (c ascending), so the distances are bit-identical
+        d0[r] = fmaf(rv.w, e0[3], fmaf(rv.z, e0[2], fmaf(rv.y, e0[1], fmaf(rv.x, e0[0], d0[r]))));
+        d1[r] = fmaf(rv.w, e1[3], fmaf(rv.z, e1[2], fmaf(rv.y, e1[1], fmaf(rv.x, e1[0], d1[r]))));
       }
     }
     __syncthreads();     // s_x2 visible
