@@ -382,23 +382,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn fa_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
 // {64 * heads columns, rows, batch} view of a [batch * rows, ld] bf16 activation; box = 64 x 128 x 1
 static int make_map(EncodeTiledFn enc, CUtensorMap* m, const void* base, int heads, int rows, int batch, int ld) {
   cuuint64_t dims[3] = {(cuuint64_t)heads * FA_HD, (cuuint64_t)rows, (cuuint64_t)batch};
@@ -425,7 +408,7 @@ bool attention_tcgen05_eligible(const AttnDesc& d) {
 }
 
 int launch_attention_tcgen05(const AttnDesc& d, cudaStream_t stream) {
-  EncodeTiledFn enc = fa_encode_fn();
+  EncodeTiledFn enc = get_tensor_map_encoder();
   if (!enc) return set_error(TASTE_E_NO_DEVICE, "cuTensorMapEncodeTiled entry point unavailable");
   CUtensorMap mq, mk, mv;
   int rc;

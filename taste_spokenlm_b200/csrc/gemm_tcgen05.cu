@@ -628,11 +628,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const _
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
+EncodeTiledFn get_tensor_map_encoder() {
   static EncodeTiledFn fn = nullptr;
   static bool tried = false;
   if (!tried) {
@@ -752,7 +748,7 @@ int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
                      d.n, d.taps);
   if (d.rows_out <= 0 || d.batches <= 0) return 0;
   if (d.epilogue == EPI_GELU_POS_F32 && !d.pos) return set_error(TASTE_E_ARG, "gemm: pos table missing");
-  EncodeTiledFn enc = get_encode_fn();
+  EncodeTiledFn enc = get_tensor_map_encoder();
   if (!enc) return set_error(TASTE_E_NO_DEVICE, "cuTensorMapEncodeTiled entry point unavailable");
 
   // tile shape: CTA pairs (256 x 256) when there is at least one wave of pair tiles, else single-CTA 128 x {256,128}

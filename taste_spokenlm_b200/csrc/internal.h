@@ -31,6 +31,12 @@ struct ProfScope {
   int slot_;
 };
 
+// ---- TMA descriptors: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda needed) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_tensor_map_encoder();   // gemm_tcgen05.cu; nullptr when the entry point is unavailable
+
 // ---- GEMM (gemm_tcgen05.cu) ----
 enum GemmEpilogue {
   EPI_BF16 = 0,          // out bf16 = acc + bias

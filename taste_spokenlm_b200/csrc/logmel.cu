@@ -214,22 +214,24 @@ int launch_logmel(const taste_weights_t& w, const float* wav, const int32_t* n_s
   float* logspec = feats_f32 ? feats_f32 : scratch_logspec;
   TASTE_CUDA_OK(cudaMemsetAsync(scratch_max, 0, sizeof(unsigned int) * batch, stream));
   dim3 grid((TASTE_N_FRAMES + LM_FRAMES - 1) / LM_FRAMES, batch);
-  // algorithmic bytes of the whole front-end: waveform in + features out (3.456 MB per utterance),
-  // booked on the tile kernel; the finish pass is booked with its own read+write
   const double feat_elems = double(batch) * TASTE_N_FRAMES * TASTE_N_MELS;
-  ProfScope ps1(stream, KC_LOGMEL_TILE, double(batch) * TASTE_N_FRAMES * (2.0 * 2 * 199 * 101 + 2.0 * 394),
-                double(batch) * TASTE_N_SAMPLES * 4.0 + feat_elems * 4.0);
-  logmel_tile_kernel<<<grid, LM_THREADS, LM_SMEM, stream>>>(wav, n_samples, wav_stride, w.dft_cos, w.dft_sin, w.hann,
-                                                            w.mel_start, w.mel_count, w.mel_weight, logspec, scratch_max);
-  TASTE_CUDA_OK(cudaGetLastError());
-  ps1.~ProfScope();
-  ps1.slot_ = -1;
-  dim3 grid2(48, batch);
-  ProfScope ps2(stream, KC_LOGMEL_FINISH, feat_elems * 3.0,
-                feat_elems * (4.0 + (feats_f32 ? 4.0 : 0.0) + (feats_bf16 ? 2.0 : 0.0)));
-  logmel_finish_kernel<<<grid2, 256, 0, stream>>>(logspec, scratch_max, feats_f32,
-                                                  static_cast<__nv_bfloat16*>(feats_bf16));
-  TASTE_CUDA_OK(cudaGetLastError());
+  {
+    // algorithmic bytes of the whole front-end: waveform in + features out (3.456 MB per utterance),
+    // booked on the tile kernel; the finish pass is booked with its own read + write
+    ProfScope ps(stream, KC_LOGMEL_TILE, double(batch) * TASTE_N_FRAMES * (2.0 * 2 * 199 * 101 + 2.0 * 394),
+                 double(batch) * TASTE_N_SAMPLES * 4.0 + feat_elems * 4.0);
+    logmel_tile_kernel<<<grid, LM_THREADS, LM_SMEM, stream>>>(wav, n_samples, wav_stride, w.dft_cos, w.dft_sin, w.hann,
+                                                              w.mel_start, w.mel_count, w.mel_weight, logspec, scratch_max);
+    TASTE_CUDA_OK(cudaGetLastError());
+  }
+  {
+    dim3 grid2(48, batch);
+    ProfScope ps(stream, KC_LOGMEL_FINISH, feat_elems * 3.0,
+                 feat_elems * (4.0 + (feats_f32 ? 4.0 : 0.0) + (feats_bf16 ? 2.0 : 0.0)));
+    logmel_finish_kernel<<<grid2, 256, 0, stream>>>(logspec, scratch_max, feats_f32,
+                                                    static_cast<__nv_bfloat16*>(feats_bf16));
+    TASTE_CUDA_OK(cudaGetLastError());
+  }
   return 0;
 }
 
