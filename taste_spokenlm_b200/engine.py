@@ -309,6 +309,23 @@ class TowerEngine(FrontendEngine):
                                                  _lib.ptr(out), self._stream()), "taste_rvq_decode_f32")
         return out.reshape(*shape, out.shape[-1])
 
+    def map_to_llm_tokens(self, asr_indices, asr_word_ids, asr_token_lengths, llm_word_ids, llm_token_lengths):
+        """extract_vq epilogue (MT:1438-1450, MT:1877-1881): asr-token indices [B,T,Q] -> llm-token indices [B,L,Q]
+        (-1 where an llm token is not the first token of a word that also starts an asr word)."""
+        dev = self.device
+        idx = asr_indices.to(device=dev, dtype=torch.int64).contiguous()
+        B, T, Q = idx.shape
+        awid = asr_word_ids.to(device=dev, dtype=torch.int32)[:, :T].contiguous()
+        lwid = llm_word_ids.to(device=dev, dtype=torch.int32).contiguous()
+        L = lwid.shape[1]
+        alen = asr_token_lengths.to(device=dev, dtype=torch.int32).contiguous()
+        llen = llm_token_lengths.to(device=dev, dtype=torch.int32).contiguous()
+        out = torch.empty(B, L, Q, dtype=torch.int64, device=dev)
+        _lib.check(self.lib.taste_map_to_llm_tokens(_lib.ptr(idx), _lib.ptr(awid), _lib.ptr(alen), _lib.ptr(lwid),
+                                                    _lib.ptr(llen), B, T, L, Q, _lib.ptr(out), self._stream()),
+                   "taste_map_to_llm_tokens")
+        return out
+
     def assemble_tokens(self, ids_dev: torch.Tensor, lens32: torch.Tensor, cu: torch.Tensor, sum_tokens: int):
         """Packed assembled ids on the device (MT:144-152); see taste_assemble_tokens."""
         B, Tmax = ids_dev.shape

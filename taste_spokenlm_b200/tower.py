@@ -355,11 +355,26 @@ class TasteAudioTowerB200(nn.Module):
         return result
 
 
-def install(patch_frontend: bool = True) -> None:
+def extract_vq(model, asr_token_ids, asr_token_lengths, asr_word_ids, llm_token_ids, llm_token_lengths, llm_word_ids,
+               audio_features, audio_feature_lengths):
+    """Drop-in for `TasteForCausalLM.extract_vq` (MT:1859-1881) when `model.audio_tower` is a `TasteAudioTowerB200`:
+    same arguments, same `(asr_indices, llm_indices)` result; the word-start mapping (MT:1438-1450) runs as one CUDA
+    kernel instead of a [B,L,T] matrix, two cumsums and a float bmm.  `install(patch_extract_vq=True)` binds it."""
+    tower = model.audio_tower if hasattr(model, "audio_tower") else model
+    enc = tower(asr_token_ids, asr_token_lengths, audio_features, audio_feature_lengths, asr_word_ids=asr_word_ids)
+    asr_indices = enc["quantized_indices"]
+    llm_indices = tower.engine().map_to_llm_tokens(asr_indices, asr_word_ids, asr_token_lengths, llm_word_ids,
+                                                   llm_token_lengths)
+    return asr_indices, llm_indices
+
+
+def install(patch_frontend: bool = True, patch_extract_vq: bool = True) -> None:
     """Swap the reference's classes for the B200 ones (needs `taste_speech` importable).  See INTEGRATION.md."""
     import importlib
     mt = importlib.import_module("taste_speech.modeling_taste")
     mt.TasteAudioTower = TasteAudioTowerB200
+    if patch_extract_vq and hasattr(mt, "TasteForCausalLM"):
+        mt.TasteForCausalLM.extract_vq = extract_vq
     if patch_frontend:
         from .frontend import WhisperFrontendB200
         for modname in ("taste_speech.processing_taste", "taste_speech.data.dataset",
