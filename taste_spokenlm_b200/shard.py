@@ -119,3 +119,80 @@ def tokenize_corpus(engine, corpus, world_size: int, rank: int, batch_size: int 
     if not gather:
         return _unpack([(hdr, flat.cpu().reshape(-1, num_q))])
     return gather_indices(hdr.to(engine.device), flat.to(engine.device), num_q, engine.device)
+
+
+class ShardWriter:
+    """Streaming, resumable result writer for the corpus job.
+
+    The reference buffers every result in RAM and writes one HF dataset per rank at the very end
+    (`Dataset.from_list(self.results).save_to_disk(f"{output_dir}/part-{LOCAL_RANK}")`, XV:70, XV:161-162): a crash loses
+    the rank's whole shard.  This writer flushes an Arrow IPC file every `flush_every` utterances under
+    `<out_dir>/part-<rank>/` with the reference's column names (`llm_indices`, `llm_token_ids`, `llm_token_lengths`,
+    `llm_word_ids`; XV:51-70) plus `utt_id`, and keeps `manifest.json` (files + utterance ids done) so a restarted rank
+    skips what is already on disk.
+    """
+
+    COLUMNS = ("utt_id", "llm_indices", "llm_token_ids", "llm_token_lengths", "llm_word_ids")
+
+    def __init__(self, out_dir: str, rank: int, flush_every: int = 1024):
+        import json
+        import os
+        self.dir = os.path.join(out_dir, f"part-{rank}")
+        os.makedirs(self.dir, exist_ok=True)
+        self.flush_every = flush_every
+        self._manifest_path = os.path.join(self.dir, "manifest.json")
+        self.manifest = {"files": [], "done": []}
+        if os.path.exists(self._manifest_path):
+            with open(self._manifest_path) as f:
+                self.manifest = json.load(f)
+        self._done = set(self.manifest["done"])
+        self._rows = []
+
+    def is_done(self, utt_id: int) -> bool:
+        return int(utt_id) in self._done
+
+    def pending(self, utt_ids) -> np.ndarray:
+        """The subset of `utt_ids` that still has to be tokenized (order preserved)."""
+        return np.asarray([u for u in utt_ids if int(u) not in self._done], dtype=np.int64)
+
+    def add(self, utt_id: int, llm_indices, llm_token_ids, llm_word_ids) -> None:
+        """One utterance: llm_indices [L, Q] (ints, -1 on non-word-start tokens), llm_token_ids [L], llm_word_ids [L]."""
+        li = np.asarray(llm_indices, dtype=np.int64)
+        self._rows.append((int(utt_id), li.tolist(), np.asarray(llm_token_ids, dtype=np.int64).tolist(), int(li.shape[0]),
+                           np.asarray(llm_word_ids, dtype=np.int64).tolist()))
+        if len(self._rows) >= self.flush_every:
+            self.flush()
+
+    def flush(self) -> None:
+        import json
+        import os
+        import pyarrow as pa
+        if not self._rows:
+            return
+        cols = list(zip(*self._rows))
+        table = pa.table({name: list(col) for name, col in zip(self.COLUMNS, cols)})
+        name = f"data-{len(self.manifest['files']):05d}.arrow"
+        tmp = os.path.join(self.dir, name + ".tmp")
+        with pa.OSFile(tmp, "wb") as sink, pa.ipc.new_file(sink, table.schema) as w:
+            w.write_table(table)
+        os.replace(tmp, os.path.join(self.dir, name))              # the file exists completely or not at all
+        self.manifest["files"].append(name)
+        self.manifest["done"].extend(int(u) for u in cols[0])
+        self._done.update(int(u) for u in cols[0])
+        with open(self._manifest_path + ".tmp", "w") as f:
+            json.dump(self.manifest, f)
+        os.replace(self._manifest_path + ".tmp", self._manifest_path)
+        self._rows = []
+
+    def close(self) -> None:
+        self.flush()
+
+    def read_all(self):
+        """All rows written so far as a list of dicts (for tests / small shards)."""
+        import os
+        import pyarrow as pa
+        out = []
+        for name in self.manifest["files"]:
+            with pa.memory_map(os.path.join(self.dir, name)) as src:
+                out.extend(pa.ipc.open_file(src).read_all().to_pylist())
+        return out

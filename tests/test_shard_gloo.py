@@ -89,3 +89,31 @@ def test_gather_indices_single_process():
     assert torch.equal(got[2][1].to(torch.int64), _fake_indices(2, 7))
     hdr0, flat0 = shard.pack_results([], [])
     assert shard.gather_indices(hdr0, flat0, 4) == []
+
+
+def test_shard_writer_streams_and_resumes(tmp_path):
+    w = shard.ShardWriter(str(tmp_path), rank=1, flush_every=3)
+    rng = np.random.default_rng(0)
+    ref = {}
+    for u in range(7):
+        L = int(rng.integers(1, 9))
+        li = rng.integers(-1, 512, (L, 4))
+        ref[u] = li
+        w.add(u, li, rng.integers(0, 32000, L), np.arange(L))
+    assert len(w.manifest["files"]) == 2 and sorted(w.manifest["done"]) == [0, 1, 2, 3, 4, 5]      # 7th still buffered
+    # a crash here loses only the unflushed utterance; a restarted rank skips the six on disk
+    w2 = shard.ShardWriter(str(tmp_path), rank=1, flush_every=3)
+    assert w2.pending(range(9)).tolist() == [6, 7, 8]
+    assert w2.is_done(5) and not w2.is_done(6)
+    for u in (6, 7, 8):
+        L = 4
+        li = rng.integers(-1, 512, (L, 4))
+        ref[u] = li
+        w2.add(u, li, rng.integers(0, 32000, L), np.arange(L))
+    w2.close()
+    rows = w2.read_all()
+    assert [r["utt_id"] for r in rows] == list(range(9))
+    for r in rows:
+        assert set(r) == set(shard.ShardWriter.COLUMNS)
+        assert np.array_equal(np.asarray(r["llm_indices"]), ref[r["utt_id"]])
+        assert r["llm_token_lengths"] == len(r["llm_token_ids"]) == len(r["llm_word_ids"])
