@@ -1,13 +1,15 @@
 #!/bin/bash
-# Staged GPU check: each stage under its own timeout, logs into gpurun_out/.
 set -u
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
-for t in test_layernorm test_logmel test_rvq test_word_pool test_map test_attention test_gemm; do
-  timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -k "$t" --timeout 300 > gpurun_out/pytest_$t.log 2>&1
-  echo "$t exit $?" | tee -a gpurun_out/summary.txt
-  tail -3 gpurun_out/pytest_$t.log
-done
-timeout 600 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1
-echo "smoke exit $?" | tee -a gpurun_out/summary.txt
-tail -5 gpurun_out/smoke.log
+timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x --timeout 300 -k "gemm" > gpurun_out/pytest_gemm.log 2>&1
+echo "pytest gemm exit $?"; tail -5 gpurun_out/pytest_gemm.log
+timeout 1200 python -m pytest tests -m gpu -q --timeout 600 -k "not gemm" > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest rest exit $?"; tail -5 gpurun_out/pytest_gpu.log
+timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err
+echo "bench exit $?"; tail -c 1500 gpurun_out/bench.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench.json'))
+print('value',d['value'],'ms/step',d['ms_per_step'],'e2e',d['e2e']['value'], d['clocks'])
+for s in d['stages'][:6]: print(s['kernel'], round(s['ms_per_step'],2), round(s['achieved'],1), round(s['frac'],3))
+PY
