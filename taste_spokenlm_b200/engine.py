@@ -352,6 +352,7 @@ class TowerEngine(FrontendEngine):
         tokens = self.assemble_tokens(ids_dev, lens32, cu, sum_tokens)
         dec = self.aggregate(h_last, h_t, tokens, cu, sum_tokens, max_tokens)
         z = self.word_pool(dec, cu, wid_dev, lens32, B, Tmax)
+        self._last_decoder = (dec, cu_np)        # for the secondary WhisperAudioJointEncoderSegmenter interface
         if skip_vq:                                                                      # MT:180,205
             return z, None
         Tm = int(lengths_host.max())             # generate_mask_from_length width (modules_taste/utils.py:5-8)

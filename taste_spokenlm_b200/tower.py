@@ -113,6 +113,48 @@ class WhisperAudioJointEncoderSegmenterB200(nn.Module):
         self.device = device
         return super().to(device)
 
+    _tower_ref = None            # weak reference to the owning TasteAudioTowerB200 (which owns the kernel engine)
+
+    def forward(self, audio_features, audio_features_lengths, asr_token_ids=None, asr_token_lengths=None,
+                asr_word_ids=None, whisper_text_token=None, whisper_text_token_len=None, words_index=None,
+                word_ids=None, **kwargs):
+        """Secondary interface of the reference (JES:336-416): `(encoded_results, segmented_results)`.
+
+        `whisper_text_token` is the assembled sequence prefix(4) ++ ids ++ EOS (MT:144-151) and
+        `whisper_text_token_len = T + 5`.  `segmented_feats` is `[B, Tmax + 1, D]` with lengths `T + 1` exactly as the
+        reference returns it before the tower drops the EOS slot (MT:170-172); slot `T_b` holds the un-pooled decoder
+        state of that position, which no caller consumes."""
+        if self._tower_ref is None or self._tower_ref() is None:
+            raise _lib.TasteError("WhisperAudioJointEncoderSegmenterB200 is not attached to a TasteAudioTowerB200")
+        if words_index is not None:
+            raise NotImplementedError("pass `word_ids`; explicit `words_index` lists are not supported")
+        if whisper_text_token is None or whisper_text_token_len is None or word_ids is None:
+            raise AssertionError("joint encoder segmenter is word-level, please pass `words_index` or `word_ids` properly!")
+        tower = self._tower_ref()
+        eng = tower.engine()
+        dev = eng.device
+        feats = audio_features.detach()
+        if feats.shape[1] < _lib.N_FRAMES:
+            feats = torch.nn.functional.pad(feats, (0, 0, 0, _lib.N_FRAMES - feats.shape[1]))
+        if feats.dtype not in (torch.float32, torch.bfloat16):
+            feats = feats.float()
+        h_last, h_t = eng.encode(feats.to(dev).contiguous())
+        ids = whisper_text_token.detach()[:, 4:-1].to(device=dev, dtype=torch.int64).contiguous()
+        lens_host = (whisper_text_token_len.detach().cpu().numpy().astype("int64") - 5)
+        wid = word_ids.detach().to(device=dev, dtype=torch.int32).contiguous()
+        z, _ = eng.segment_and_quantize(h_last, h_t, ids, wid, lens_host, skip_vq=True)
+        dec, cu = eng._last_decoder
+        B, Tmax, D = z.shape
+        seg = torch.zeros(B, Tmax + 1, D, dtype=z.dtype, device=dev)
+        seg[:, :Tmax] = z
+        rows = torch.as_tensor(cu[1:] - 1, device=dev, dtype=torch.int64)            # assembled position 4 + T_b
+        seg[torch.arange(B, device=dev), torch.as_tensor(lens_host, device=dev)] = dec[rows]
+        lens1 = torch.as_tensor(lens_host + 1, device=dev, dtype=whisper_text_token_len.dtype)
+        encoded = {"encoded_feats": {"last_hidden": h_last, str(tower.cfg.target_hidden_layer): h_t},
+                   "encoded_feats_lengths": audio_features_lengths // 2 if audio_features_lengths is not None else None}
+        segmented = {"segmented_feats": seg, "segmented_feat_lengths": lens1}
+        return encoded, segmented
+
 
 class _Codebook(nn.Module):
     """Buffers of EuclideanCodebook (VQ:319-327)."""
@@ -277,6 +319,8 @@ class TasteAudioTowerB200(nn.Module):
             self.quantization_on = False
         self.audio_dropout_ratio = audio_dropout_ratio
         self.add_eos = True
+        import weakref
+        self.audio_joint_encoder_segmenter._tower_ref = weakref.ref(self)
         self._engine: Optional[TowerEngine] = None
         self._engine_key = None
 
