@@ -2,15 +2,18 @@
 // scores and accumulators.  Serves the encoder self-attention (CW:377-394 eager semantics: softmax(q k^T) v with q
 // pre-scaled, NO mask — JES:198-203), which is 16 % of the path's FLOPs.
 //
-// One CTA owns 256 queries of one (utterance, head) as two 128-row tiles that ping-pong through the tensor pipe:
+// Persistent: one CTA per SM walks over work items of 256 queries of one (utterance, head), as two 128-row tiles:
 //   S_i = Q_i K_j^T   tcgen05.mma  SS  (M 128, N 128 keys, K 64)      -> TMEM, 128 fp32 columns per tile
-//   softmax           one thread per query row reads its S row with tcgen05.ld (no shuffles), keeps the running
-//                     max / sum in registers, writes P (bf16) back to TMEM with tcgen05.st
+//   softmax           one thread per query row reads its whole S row ONCE with tcgen05.ld (no shuffles) and hands S
+//                     back at once, keeps the running max / sum in registers, exponentiates in packed FFMA2 pairs
+//                     (MUFU ex2 for 10 of 16 pairs, a degree-3 polynomial on the FMA pipe for the other 6) and
+//                     writes P (bf16) back to TMEM with tcgen05.st
 //   O_i += P_i V_j    tcgen05.mma  TS  (A = P from TMEM, B = V tile, MN-major; M 128, N 64, K 128 keys)
-// While warpgroup i exponentiates, the MMA warp runs the other tile's GEMMs.  K/V tiles arrive by TMA (128-byte
-// swizzle) through a 4-stage mbarrier ring straight from the packed [rows, 3*D] QKV activation.  The accumulator is
-// rescaled only when a row's maximum grows by more than 2^8 (the stale maximum keeps exp2 arguments <= 8, exact in
-// fp32 / bf16 range), so the O read-modify-write in TMEM is rare after the first key block.
+// Each tile has its own MMA-issuing warp, so the next block's QK^T of a tile runs under that tile's exponentials and
+// under the other tile's GEMMs.  Q (double buffered) and K/V (4-stage mbarrier ring) arrive by TMA (128-byte swizzle)
+// straight from the packed [rows, 3*D] QKV activation.  The accumulator is rescaled only when a row's maximum grows by
+// more than 2^8 (the stale maximum keeps exp2 arguments <= 8, exact in fp32 / bf16 range), so the O read-modify-write
+// in TMEM is rare after the first key block.
 //
 // Roles (352 threads): warps 0-3 softmax tile 0, warps 4-7 softmax tile 1 (warp w owns TMEM lanes 32*(w%4)..+31),
 // warp 8 TMA producer, warp 9 MMA issuer of tile 0 + TMEM allocator, warp 10 MMA issuer of tile 1.

@@ -5,8 +5,10 @@
 // through the multi-tap A addressing, the two stem convolutions as implicit GEMMs (JES:174-175): tap t of the k=3
 // kernel is a GEMM over the same activations shifted by one row, and the zero padding is TMA out-of-bounds fill.
 //
-// Roles (256 threads, 1 CTA / SM):  warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4-7 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31 = rows of the 128-row tile).
+// Two kernels share this file: the CTA-pair kernel (cta_group::2, 256 x 256 tiles, 8 epilogue warps, coalesced
+// epilogues, optional LayerNorm folding) that carries the encoder, and the single-CTA kernel below it in the file for
+// small problems.  Roles of the single-CTA kernel (256 threads, 1 CTA / SM):  warp 0 = TMA producer, warp 1 = MMA
+// issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31 = rows of the tile).
 #include <stdio.h>
 #include <stdlib.h>
 
