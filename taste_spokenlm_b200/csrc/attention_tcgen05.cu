@@ -15,8 +15,13 @@
 // more than 2^8 (the stale maximum keeps exp2 arguments <= 8, exact in fp32 / bf16 range), so the O read-modify-write
 // in TMEM is rare after the first key block.
 //
-// Roles (352 threads): warps 0-3 softmax tile 0, warps 4-7 softmax tile 1 (warp w owns TMEM lanes 32*(w%4)..+31),
-// warp 8 TMA producer, warp 9 MMA issuer of tile 0 + TMEM allocator, warp 10 MMA issuer of tile 1.
+// Roles (384 threads, three warpgroups): warps 0-3 softmax tile 0, warps 4-7 softmax tile 1 (warp w owns TMEM lanes
+// 32*(w%4)..+31), warp 8 TMA producer, warp 9 MMA issuer of tile 0 + TMEM allocator, warp 10 MMA issuer of tile 1,
+// warp 11 idle (it completes the third warpgroup so that setmaxnreg can move registers: softmax threads 232, the
+// rest 40 - the softmax thread holds a 128-score row and schedules its exp2 phase far better with the extra 64).
+// The two tiles' exp2 phases are ping-ponged with named barriers: left alone they drift into lock-step (measured with
+// the in-kernel timeline), where both warps of a scheduler stall on the MUFU queue and the block period grows by a
+// third.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -28,10 +33,13 @@ constexpr int FA_BQ = 128;          // query rows per tile (2 tiles per work ite
 constexpr int FA_BK = 128;          // keys per block
 constexpr int FA_HD = 64;
 constexpr int FA_STAGES = 4;
-constexpr int FA_THREADS = 352;
+constexpr int FA_THREADS = 384;          // 12 warps: three full warpgroups (setmaxnreg is per warpgroup)
 #ifndef FA_POLY
 #define FA_POLY 6                   // of every 16 score pairs, this many take the polynomial exp2 path
 #endif
+// VAR bits: 2 = setmaxnreg (softmax warpgroups 216, others 64), 8 = 232 / 40 instead, 16 = ping-pong of the two
+// tiles' exp2 phases, 32 = hand the turn over one chunk early, 4 = timeline trace
+constexpr int FA_VAR_DEFAULT = 2 | 8 | 16 | 32;
 constexpr uint32_t FA_TILE_BYTES = FA_BQ * FA_HD * 2;      // 16 KB: one Q, K or V tile
 // Q is double buffered (2 x 2 tiles) so the next work item's queries load under the current item's last blocks
 constexpr size_t FA_SMEM = 1024 + size_t(4 + 2 * FA_STAGES) * FA_TILE_BYTES + 256;
@@ -42,7 +50,7 @@ constexpr uint32_t FA_COL_O = 256;    // O0 [256,320) O1 [320,384)
 constexpr uint32_t FA_COL_P = 384;    // P0 [384,448) P1 [448,512)   (bf16 pairs: 64 columns per 128 keys)
 
 struct FaParams {
-  long long* dbg;      // timeline trace (VAR 4 only)
+  long long* dbg;      // timeline trace (VAR bit 2 only)
   __nv_bfloat16* o;
   int ldo;
   int q_len, kv_len;
@@ -51,7 +59,7 @@ struct FaParams {
 
 #define FA_TRACE(slot, idx)                                                      \
   do {                                                                           \
-    if (VAR == 4 && p.dbg && blockIdx.x == 0 && lane == 0 && (idx) < 256)        \
+    if ((VAR & 4) && p.dbg && blockIdx.x == 0 && lane == 0 && (idx) < 256)       \
       p.dbg[(slot) * 256 + (idx)] = clock64();                                   \
   } while (0)
 
@@ -114,8 +122,16 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
 
   // Producer and MMA warps run warp-uniform loops and elect one lane around the TMA / tcgen05 instructions (inside an
   // `if (lane == 0)` region every UTCHMMA is wrapped in an ELECT loop: ~90 cycles per MMA, measured with FA_TRACE).
-  if (warp == 8) {
+  // VAR bit 1: register reallocation between warpgroups (the softmax threads hold a whole 128-score row + the prefetched
+  // chunk of the next block; the TMA / MMA warps need almost nothing).  256 x 216 + 128 x 64 <= 384 x 168.
+  // (the instruction sits at the head of each role's branch: ptxas budgets registers per region it dominates)
+#define FA_REGS_SMALL() do { if constexpr ((VAR & 2) != 0) { if constexpr ((VAR & 8) != 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;"); else asm volatile("setmaxnreg.dec.sync.aligned.u32 64;"); } } while (0)
+#define FA_REGS_LARGE() do { if constexpr ((VAR & 2) != 0) { if constexpr ((VAR & 8) != 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;"); else asm volatile("setmaxnreg.inc.sync.aligned.u32 216;"); } } while (0)
+  if (warp == 11) {
+    FA_REGS_SMALL();        // idle: only completes the third warpgroup
+  } else if (warp == 8) {
     // ===================== TMA producer =====================
+    FA_REGS_SMALL();
     int stage = 0;
     uint32_t phase = 0;
     for (int it = 0; it < my_items; ++it) {
@@ -153,6 +169,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
     // ===================== MMA issuers: warp 9 drives query tile 0, warp 10 tile 1 =====================
     // One issuing thread per tile, so neither tile's GEMMs ever queue behind a barrier that only the other tile's
     // softmax warps can satisfy (with a single issuer and a fixed wait order the two warpgroups throttled each other).
+    FA_REGS_SMALL();
     const int i = warp - 9;
     constexpr uint32_t idesc_qk = umma_idesc(FA_BQ, FA_BK, 1, 0, 0);        // A, B K-major
     constexpr uint32_t idesc_pv = umma_idesc(FA_BQ, FA_HD, 1, 0, 1);        // A from TMEM, B (V) MN-major
@@ -213,6 +230,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
     }
   } else {
     // ===================== softmax + output (warps 0-7) =====================
+    FA_REGS_LARGE();
     const int i = warp >> 2;                        // query tile
     const int q = warp & 3;                         // TMEM lane quarter
     const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16);
@@ -220,6 +238,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
     const uint32_t t_o = lane_base + FA_COL_O + uint32_t(i * FA_HD);
     const uint32_t t_p = lane_base + FA_COL_P + uint32_t(i * 64);
     const float kLog2e = 1.4426950408889634f;
+    if constexpr ((VAR & 16) != 0) {
+      if (i == 1 && total_g > 0) asm volatile("bar.arrive 1, 256;" ::: "memory");      // tile 0 goes first
+    }
     int g = 0;
     for (int it = 0; it < my_items; ++it) {
       const int w = int(blockIdx.x) + it * int(gridDim.x);
@@ -269,12 +290,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
             for (int e = 0; e < 32; ++e)
               if (c * 32 + e >= valid) r[c][e] = 0xff800000u;      // -inf
         }
-        float mx = -INFINITY;
+        // four independent chains (a single chain of 64 dependent FMNMX3 costs ~400 cycles per block)
+        float mxc[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
           for (int e = 0; e < 32; ++e)
-            mx = fmaxf(mx, __uint_as_float(r[c][e]));
+            mxc[c] = fmaxf(mxc[c], __uint_as_float(r[c][e]));
+        const float mx = fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3]));
         FA_TRACE(i, g * 8 + 2);
         const bool grow = mx > m_used + 5.545177f;     // 8 in log2 units; first block: m_used = -inf
         const bool any_grow = __any_sync(0xffffffffu, grow);
@@ -289,6 +312,13 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
         const uint64_t negm2 = f2_pack(neg_m, neg_m);
         const uint64_t log2e2 = f2_pack(kLog2e, kLog2e);
         uint64_t sum2 = f2_pack(0.f, 0.f);
+        // VAR bit 4: ping-pong.  The two tiles' exp2 phases alternate (named barriers 1 / 2, FA3-style) instead of
+        // drifting into lock-step, where both warps of a scheduler fight for the MUFU queue and neither feeds the FMA
+        // pipe; the other tile's TMEM loads, row maximum and waits run under this tile's exponentials.
+        if constexpr ((VAR & 16) != 0) {
+          if (i == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+          else asm volatile("bar.sync 2, 256;" ::: "memory");
+        }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[16];
@@ -335,6 +365,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
             }
           }
           tmem_st_32x32b_x16(t_p + uint32_t(c * 16), pk);
+          if constexpr ((VAR & 16) != 0) {
+            if (c == ((VAR & 32) ? 2 : 3)) {            // hand the turn over (bit 5: one chunk early)
+              if (i == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");
+              else if (g + 1 < total_g) asm volatile("bar.arrive 1, 256;" ::: "memory");
+            }
+          }
         }
         float sum0, sum1;
         f2_unpack(sum2, sum0, sum1);
@@ -421,12 +457,13 @@ int launch_attention_tcgen05(const AttnDesc& d, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
 #define FA_CFG(V, P) TASTE_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<V, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM))
-    FA_CFG(0, FA_POLY); FA_CFG(4, FA_POLY); FA_CFG(0, 0);
+    FA_CFG(FA_VAR_DEFAULT, FA_POLY); FA_CFG(FA_VAR_DEFAULT, 0); FA_CFG(FA_VAR_DEFAULT | 4, FA_POLY);
+    FA_CFG(0, FA_POLY); FA_CFG(10, FA_POLY); FA_CFG(26, FA_POLY);
 #undef FA_CFG
     configured = true;
   }
   const char* ev = getenv("TASTE_FA_VAR");
-  const int var = ev ? atoi(ev) : 0;
+  const int var = ev ? atoi(ev) : -1;
   FaParams p;
   p.dbg = g_fa_trace;
   p.o = static_cast<__nv_bfloat16*>(d.o);
@@ -448,9 +485,15 @@ int launch_attention_tcgen05(const AttnDesc& d, cudaStream_t stream) {
   ProfScope ps(stream, d.kclass == KC_ATTN_ENC ? KC_ATTN_ENC : KC_ATTN_TC, 4.0 * pairs * FA_HD * d.heads,
                2.0 * FA_HD * d.heads * double(d.batch) * (2.0 * d.q_len + 2.0 * d.kv_len));
   const char* ep = getenv("TASTE_FA_POLY");          // A/B knob: "0" = every exponential on the MUFU
-  if (var == 4) attention_tcgen05_kernel<4, FA_POLY><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
-  else if (ep && atoi(ep) == 0) attention_tcgen05_kernel<0, 0><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
-  else attention_tcgen05_kernel<0, FA_POLY><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, p);
+  // variants without register reallocation run 11 warps (no idle twelfth warp)
+#define FA_GO(V, P) attention_tcgen05_kernel<V, P><<<grid, ((V) & 2) ? FA_THREADS : FA_THREADS - 32, FA_SMEM, stream>>>(mq, mk, mv, p)
+  if (var == 4) FA_GO(FA_VAR_DEFAULT | 4, FA_POLY);        // timeline trace (scripts/attn_trace.py)
+  else if (var == 0) FA_GO(0, FA_POLY);                    // round-1 v7 scheduling: 168 registers, free-running tiles
+  else if (var == 10) FA_GO(10, FA_POLY);                  // + setmaxnreg 232 / 40
+  else if (var == 26) FA_GO(26, FA_POLY);                  // + strict ping-pong
+  else if (ep && atoi(ep) == 0) FA_GO(FA_VAR_DEFAULT, 0);
+  else FA_GO(FA_VAR_DEFAULT, FA_POLY);
+#undef FA_GO
   TASTE_CUDA_OK(cudaGetLastError());
   return 0;
 }
