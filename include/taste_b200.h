@@ -188,6 +188,23 @@ int taste_map_to_llm_tokens(const int64_t* asr_indices, const int32_t* asr_word_
                             const int32_t* llm_word_ids, const int32_t* llm_lengths, int batch, int tmax, int lmax,
                             int num_q, int64_t* llm_indices, void* stream);
 
+/* --- (f)2: corpus ingest, `resampler(speech_pt).mean(0)` of process_one_sample (DS:52-60) --------------------- */
+/* torchaudio.transforms.Resample(orig_sr, 16000) (sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99; third
+ * party, restated in oracle/taste_oracle.py) followed by the channel mean, for a batch of decoded PCM arrays.
+ * in: fp32, utterance b is [channels[b], n_in[b]] row-major at in + in_offsets[b] (in_offsets int64 [batch+1]).
+ * orig_reduced / new_reduced: the two rates divided by their gcd; width, taps: the polyphase kernel of
+ * functional._get_sinc_resample_kernel in sparse form - phase p uses taps[p*taps_ld .. +taps_per_phase) against
+ * xpad[f*orig + tap_start[p] + k] (xpad = signal left-padded with `width` zeros).  Identity (orig == new): 1, 1, 0,
+ * taps {1}, tap_start {0}.  Output row b of wav [batch, wav_stride]: the first min(ceil(new*n/orig), wav_stride)
+ * samples (the rest of the row is not written: taste_logmel_f32 treats it as zero given n_samples); n_out
+ * (nullable) int32 [batch] = ceil(new*n/orig).  max_out bounds the grid (max over b of the output length);
+ * total_in_elems / total_out_elems are used for accounting only. */
+int taste_resample_mean_f32(const float* in, const int64_t* in_offsets, const int32_t* channels, const int32_t* n_in,
+                            int batch, int orig_reduced, int new_reduced, int width, const float* taps,
+                            const int32_t* tap_start, int taps_per_phase, int taps_ld, int max_out,
+                            int64_t total_in_elems, int64_t total_out_elems, float* wav, int64_t wav_stride,
+                            int32_t* n_out, void* stream);
+
 /* --- building blocks exported for kernel-level parity tests and micro-benchmarks ---------------------------- */
 /* C[M,N] = epilogue(A[M,K] @ W[N,K]^T + bias).  A, W bf16 row-major; bias fp32 [N] (nullable).
  * epilogue: 0 = bf16 out; 1 = GELU(erf) then bf16 out; 2 = fp32 out += (residual add in place, CW:692, 702);

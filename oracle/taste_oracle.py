@@ -360,3 +360,72 @@ def map_indices_to_llm_tokens(asr_indices: torch.Tensor, asr_token_lengths: torc
         W2 = (torch.cumsum(W1, dim=-2) == 1).to(torch.int64) * M
         out[b] = W2 @ asr_indices[b].to(torch.int64) - (W2.sum(-1, keepdim=True) == 0).to(torch.int64)
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# (f)2  corpus ingest: resample to 16 kHz + channel mean + transcript word split            DS:46-95
+# --------------------------------------------------------------------------------------------------
+# Third-party arithmetic: torchaudio==2.3.1 (requirements.txt:114) `transforms.Resample(orig, new)` with its defaults
+# (sinc_interp_hann, lowpass_filter_width=6, rolloff=0.99), i.e. functional._get_sinc_resample_kernel +
+# _apply_sinc_resample_kernel.  Restated here from the published algorithm; pinned by tests/golden/resample.npz,
+# which tests/golden/make_golden.py produces with torchaudio itself running the reference's own call
+# `resampler(speech_pt).mean(0)` (DS:52-60).
+def sinc_resample_kernel(orig_freq: int, new_freq: int, lowpass_filter_width: int = 6, rolloff: float = 0.99
+                         ) -> Tuple[np.ndarray, int, int, int]:
+    """(kernel fp32 [new, 2*width+orig], width, orig, new) with orig / new reduced by their gcd."""
+    g = math.gcd(int(orig_freq), int(new_freq))
+    orig, new = int(orig_freq) // g, int(new_freq) // g
+    base = min(orig, new) * rolloff
+    width = math.ceil(lowpass_filter_width * orig / base)
+    idx = np.arange(-width, width + orig, dtype=np.float64)[None, :] / orig
+    # torch.arange(0, -new, -1) / new is evaluated in float32 (the default dtype) before it meets the float64 `idx`
+    phase = (np.arange(0, -new, -1).astype(np.float32) / np.float32(new)).astype(np.float64)[:, None]
+    t = (phase + idx) * base
+    t = np.clip(t, -lowpass_filter_width, lowpass_filter_width)
+    window = np.cos(t * math.pi / lowpass_filter_width / 2) ** 2
+    t = t * math.pi
+    with np.errstate(invalid="ignore", divide="ignore"):
+        k = np.where(t == 0, 1.0, np.sin(t) / t)
+    k = k * (window * (base / orig))
+    return k.astype(np.float32), width, orig, new
+
+
+def resample_mean(x: np.ndarray, orig_freq: int, new_freq: int = 16000) -> np.ndarray:
+    """x fp32 [C, n] -> fp32 [ceil(new*n/orig)]: torchaudio Resample on every channel, then `.mean(0)` (DS:52-60)."""
+    x = np.asarray(x, dtype=np.float32)
+    if x.ndim == 1:
+        x = x[None]                                   # DS:53-54
+    C, n = x.shape
+    if int(orig_freq) == int(new_freq):               # transforms.Resample.forward returns the input unchanged
+        return x.mean(0, dtype=np.float32) if C > 1 else x[0].copy()
+    k, width, orig, new = sinc_resample_kernel(orig_freq, new_freq)
+    K = k.shape[1]
+    xp = np.zeros((C, n + 2 * width + orig), dtype=np.float32)
+    xp[:, width: width + n] = x
+    frames = (xp.shape[1] - K) // orig + 1
+    win = np.lib.stride_tricks.sliding_window_view(xp, K, axis=1)[:, ::orig][:, :frames]      # [C, frames, K]
+    y = np.einsum("cfk,pk->cfp", win, k, dtype=np.float32).reshape(C, frames * new)
+    target = int(math.ceil(new * n / orig))
+    y = y[:, :target]
+    return (y.sum(0, dtype=np.float32) / np.float32(C)).astype(np.float32) if C > 1 else y[0]
+
+
+def split_transcript(text: str, asr_encode, llm_encode):
+    """DS:71-95: (asr_token_ids, asr_word_ids, llm_token_ids, llm_word_ids) of one transcript.
+
+    `asr_encode(word)` / `llm_encode(word)` stand for `tokenizer.encode(word, add_special_tokens=False)`.  Words are
+    the whitespace-split pieces of the stripped text, each but the first carrying a leading space.
+    """
+    import re
+    text = text.strip()
+    words = [" " + w for w in re.split(r"\s", text)]
+    words[0] = words[0].lstrip()
+    a_ids, a_wid, l_ids, l_wid = [], [], [], []
+    for i, word in enumerate(words):
+        for t in asr_encode(word):
+            a_ids.append(int(t))
+            a_wid.append(i)
+        for t in llm_encode(word):
+            l_ids.append(int(t))
+            l_wid.append(i)
+    return a_ids, a_wid, l_ids, l_wid

@@ -76,6 +76,8 @@ _SIGS = {
     "taste_rvq_encode_f32": (C.c_int, [p, p, p, C.c_int, C.c_int, C.c_int, p, p, p]),
     "taste_rvq_decode_f32": (C.c_int, [p, p, C.c_int, C.c_int, p, p]),
     "taste_map_to_llm_tokens": (C.c_int, [p, p, p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, p, p]),
+    "taste_resample_mean_f32": (C.c_int, [p, p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, p, p, C.c_int, C.c_int, C.c_int,
+                                          C.c_int64, C.c_int64, p, C.c_int64, p, p]),
     "taste_gemm_bf16": (C.c_int, [p, p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, p]),
     "taste_gemm_ex": (C.c_int, [C.POINTER(GemmEx), p]),
     "taste_encoder_set_mode": (C.c_int, [C.c_int]),

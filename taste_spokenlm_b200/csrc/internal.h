@@ -20,7 +20,7 @@ int set_error(int code, const char* fmt, ...);
 // ---- launch accounting / device timing (prof.cu) ----
 enum KernelClass {
   KC_GEMM = 0, KC_ATTN_ENC, KC_ATTN_AGG, KC_LAYERNORM, KC_CAST, KC_LOGMEL_TILE, KC_LOGMEL_FINISH, KC_EMBED,
-  KC_WORD_POOL, KC_RVQ_ENCODE, KC_RVQ_DECODE, KC_MAP_LLM, KC_ATTN_TC, KC_COUNT
+  KC_WORD_POOL, KC_RVQ_ENCODE, KC_RVQ_DECODE, KC_MAP_LLM, KC_ATTN_TC, KC_RESAMPLE, KC_COUNT
 };
 // Wrap a kernel launch: counts it and, when profiling is on, brackets it with CUDA events on `stream`.
 // flops / bytes are the ALGORITHMIC work of the launch (DESIGN.md "Kernels").
@@ -120,5 +120,11 @@ int launch_rvq_encode(const taste_weights_t& w, const float* z, const int32_t* l
                       int64_t* indices, float* quantized, cudaStream_t stream);
 int launch_rvq_decode(const taste_weights_t& w, const int64_t* indices, int n, bool project_out, float* out,
                       cudaStream_t stream);
+
+// ---- ingest (resample.cu) ----
+int launch_resample_mean(const float* in, const int64_t* in_off, const int32_t* channels, const int32_t* n_in, int batch,
+                         int orig, int nw, int width, const float* taps, const int32_t* kstart, int knz, int knz_ld,
+                         int max_out, double total_in_elems, double total_out_elems, float* wav, int64_t wav_stride,
+                         int32_t* n_out, cudaStream_t stream);
 
 }  // namespace taste

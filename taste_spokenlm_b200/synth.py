@@ -232,3 +232,48 @@ def synth_batch(seed: int, durations_s, token_counts, pad_wave_to: int = None):
         "asr_token_ids": torch.stack(ids), "asr_token_lengths": torch.tensor(token_counts, dtype=torch.int32),
         "asr_word_ids": torch.stack(wids),
     }
+
+
+class StubTokenizer:
+    """Deterministic stand-in for the Whisper / Llama tokenizers (no tokenizer files exist offline): a word is cut into
+    pieces of `piece` characters and each piece hashed into [0, vocab).  Has the two call forms process_one_sample uses
+    (DS:71-95): `.encode(word, add_special_tokens=False)` and `tok(list_of_words, add_special_tokens=False).input_ids`."""
+
+    def __init__(self, vocab: int = 50257, piece: int = 3, salt: int = 0):
+        self.vocab, self.piece, self.salt = int(vocab), int(piece), int(salt)
+
+    def encode(self, word: str, add_special_tokens: bool = False):
+        import zlib
+        return [(zlib.crc32((word[i: i + self.piece] + str(self.salt)).encode()) % self.vocab)
+                for i in range(0, len(word), self.piece)]
+
+    def __call__(self, words, add_special_tokens: bool = False):
+        class _Enc:
+            pass
+        e = _Enc()
+        e.input_ids = [self.encode(w) for w in words]
+        return e
+
+
+_WORDS = ("the quick brown fox jumps over a lazy dog while seventeen purple elephants quietly contemplate "
+          "extraordinary circumstances beyond their immediate understanding").split()
+
+
+def synth_text(seed: int, n_words: int) -> str:
+    g = torch.Generator().manual_seed(int(seed))
+    idx = torch.randint(0, len(_WORDS), (n_words,), generator=g).tolist()
+    return " ".join(_WORDS[i] for i in idx)
+
+
+def synth_pcm(seed: int, n: int, channels: int = 1):
+    """Decoded-PCM stand-in for sample['mp3']['array'] (DS:46): band-limited noise + tones, fp32 [n] or [C, n]."""
+    import numpy as np
+    g = torch.Generator().manual_seed(int(seed))
+    t = torch.arange(n, dtype=torch.float64)
+    x = 0.05 * torch.randn(channels, n, generator=g, dtype=torch.float64)
+    for _ in range(4):
+        f = float(torch.rand(1, generator=g)) * 0.2 + 0.002            # cycles per sample, below every Nyquist used
+        ph = float(torch.rand(1, generator=g)) * 6.283185307179586
+        x += 0.1 * torch.sin(2 * 3.141592653589793 * f * t + ph)[None] * torch.rand(channels, 1, generator=g, dtype=torch.float64)
+    x = x.to(torch.float32).numpy()
+    return x[0] if channels == 1 else np.ascontiguousarray(x)

@@ -166,14 +166,57 @@ def mapping_case():
     print("mapping ok", tuple(llm.shape))
 
 
+def ingest_cases(fe):
+    """(f)2: the reference's own `process_one_sample` (DS:37-113) and torchaudio's Resample on seeded PCM."""
+    import importlib
+    import torchaudio
+    DS = importlib.import_module("taste_speech.data.dataset")
+    d = {}
+    specs = [("24k_mono", 24000, 1, 6007), ("24k_stereo", 24000, 2, 4801), ("44k1_mono", 44100, 1, 9001),
+             ("8k_stereo", 8000, 2, 3001), ("48k_mono", 48000, 1, 7000), ("16k_stereo", 16000, 2, 2000),
+             ("22k05_mono", 22050, 1, 5000), ("24k_tiny", 24000, 1, 2), ("24k_one", 24000, 1, 1)]
+    meta = []
+    for i, (nm, sr, ch, n) in enumerate(specs):
+        x = synth.synth_pcm(500 + i, n, ch)
+        pt = torch.tensor(x, dtype=torch.float32)
+        if pt.dim() == 1:
+            pt = pt.unsqueeze(0)
+        y = torchaudio.transforms.Resample(orig_freq=sr, new_freq=16000)(pt).mean(0).squeeze(0).numpy()   # DS:55-60
+        d[nm] = y
+        meta.append([nm, 500 + i, sr, ch, n])
+
+    class _Proc:
+        tokenizer = synth.StubTokenizer(50257, 3, 1)
+    llm_tok = synth.StubTokenizer(128256, 4, 2)
+    samples = []
+    for j, (sr, ch, n, nwords) in enumerate([(24000, 1, 48000, 9), (44100, 2, 30011, 5), (16000, 1, 20000, 1)]):
+        x = synth.synth_pcm(600 + j, n, ch)
+        text = "  " + synth.synth_text(700 + j, nwords) + " "
+        sample = {"mp3": {"array": x, "sampling_rate": sr}, "json": {"text": text}, "s3_token": [1, 2, 3],
+                  "spk_emb": [0.1] * 8}
+        out = DS.process_one_sample(sample, resampler_dict={}, whisper_processor=_Proc(), llm_tokenizer=llm_tok,
+                                    whisper_feature_extractor=fe)
+        f = out["audio_features"]
+        d[f"s{j}_feats_sub"] = f[0, ::20, :].numpy()
+        d[f"s{j}_feats_sum"] = f.double().sum().numpy()
+        d[f"s{j}_feat_len"] = out["audio_feature_lengths"].numpy()
+        for k in ("asr_token_ids", "asr_word_ids", "llm_token_ids", "llm_word_ids"):
+            d[f"s{j}_{k}"] = out[k][0].numpy()
+        samples.append([600 + j, 700 + j, sr, ch, n, nwords])
+    np.savez_compressed(os.path.join(OUT, "ingest.npz"), meta=json.dumps(dict(resample=meta, samples=samples)), **d)
+    print("ingest ok")
+
+
 if __name__ == "__main__":
     fe = ref_shim.build_reference_frontend()
-    which = sys.argv[1:] or list(CASES) + ["frontend", "rvq", "pooling", "mapping"]
+    which = sys.argv[1:] or list(CASES) + ["frontend", "rvq", "pooling", "mapping", "ingest"]
     for name in which:
         if name in CASES:
             tower_case(name, *CASES[name], fe)
     if "frontend" in which:
         frontend_cases(fe)
+    if "ingest" in which:
+        ingest_cases(fe)
     ref_shim.build_reference_tower(d_model=128, enc_layers=1, heads=2, ffn=128, vocab=51866)   # ensures modules imported
     if "rvq" in which:
         rvq_case()
