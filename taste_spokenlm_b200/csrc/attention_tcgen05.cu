@@ -38,8 +38,15 @@ constexpr int FA_THREADS = 384;          // 12 warps: three full warpgroups (set
 #define FA_POLY 6                   // of every 16 score pairs, this many take the polynomial exp2 path
 #endif
 // VAR bits: 2 = setmaxnreg (softmax warpgroups 216, others 64), 8 = 232 / 40 instead, 16 = ping-pong of the two
-// tiles' exp2 phases, 32 = hand the turn over one chunk early, 4 = timeline trace
+// tiles' exp2 phases, 32 = hand the turn over one chunk early, 4 = timeline trace, 64 = split phases: the MUFU pairs
+// first (one tile's warp saturates the XU pipe), the turn is handed over, then the polynomial pairs (FMA pipe) run
+// under the other tile's MUFU phase, 128 = rolling prefetch: as soon as a 32-score chunk has been exponentiated its
+// registers are refilled with the NEXT block's scores (tcgen05.ld under the exponentials), so the s_full wait and the
+// TMEM load latency leave the per-tile serial loop, 256 = eight row-maximum chains instead of four, 512 = MMA issuers
+// wait parked (try_wait with a suspend hint) and the producer polls every ~1 us (their polling loops took issue slots
+// from the softmax warps on three of the four schedulers)
 constexpr int FA_VAR_DEFAULT = 2 | 8 | 16 | 32;
+constexpr int FA_VAR_SPLIT = FA_VAR_DEFAULT | 64;
 constexpr uint32_t FA_TILE_BYTES = FA_BQ * FA_HD * 2;      // 16 KB: one Q, K or V tile
 // Q is double buffered (2 x 2 tiles) so the next work item's queries load under the current item's last blocks
 constexpr size_t FA_SMEM = 1024 + size_t(4 + 2 * FA_STAGES) * FA_TILE_BYTES + 256;
@@ -142,7 +149,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
       const int b = bh / p.heads;
       const int q0 = qb * (2 * FA_BQ);
       const int qbuf = it & 1;
-      mbar_wait_relaxed(&q_empty[qbuf], uint32_t(((it >> 1) & 1) ^ 1));
+      if constexpr ((VAR & 512) != 0) mbar_wait_parked(&q_empty[qbuf], uint32_t(((it >> 1) & 1) ^ 1));
+      else mbar_wait_relaxed(&q_empty[qbuf], uint32_t(((it >> 1) & 1) ^ 1));
       if (elect_one()) {
         uint8_t* sq = sQ + size_t(2 * qbuf) * FA_TILE_BYTES;
         mbar_expect_tx(&q_full[qbuf], 2 * FA_TILE_BYTES);
@@ -151,7 +159,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
       }
       __syncwarp();
       for (int j = 0; j < n_blocks; ++j) {
-        mbar_wait_relaxed(&kv_empty[stage], phase ^ 1);
+        if constexpr ((VAR & 512) != 0) mbar_wait_parked(&kv_empty[stage], phase ^ 1);
+        else mbar_wait_relaxed(&kv_empty[stage], phase ^ 1);
         uint8_t* sk = sKV + size_t(2 * stage) * FA_TILE_BYTES;
         if (elect_one()) {
           mbar_expect_tx(&kv_full[stage], 2 * FA_TILE_BYTES);
@@ -189,17 +198,21 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
       __syncwarp();
     };
     // everything block g needs from the producer: its K/V stage and, on the first block of an item, the item's Q
+    auto wait_bar = [&](uint64_t* bar, uint32_t parity) {
+      if constexpr ((VAR & 512) != 0) mbar_wait_parked(bar, parity);
+      else mbar_wait(bar, parity);
+    };
     auto wait_inputs = [&](int g) {
       const int it = g / n_blocks;
-      if (g % n_blocks == 0) mbar_wait(&q_full[it & 1], uint32_t((it >> 1) & 1));
-      mbar_wait(&kv_full[g % FA_STAGES], uint32_t((g / FA_STAGES) & 1));
+      if (g % n_blocks == 0) wait_bar(&q_full[it & 1], uint32_t((it >> 1) & 1));
+      wait_bar(&kv_full[g % FA_STAGES], uint32_t((g / FA_STAGES) & 1));
       tc_fence_after();
     };
     if (total_g > 0) {
       wait_inputs(0);
       // tile 1 starts half a block behind tile 0 (when tile 0's first S tile has been read), so that one warpgroup
       // is in its exp2-heavy pass while the other reads / reduces scores instead of both hitting the MUFU together
-      if (i == 1) mbar_wait(&s_free[0], 0);
+      if (i == 1) wait_bar(&s_free[0], 0);
       issue_qk(0);
     }
     for (int g = 0; g < total_g; ++g) {
@@ -208,12 +221,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
       const bool more = g + 1 < total_g;
       const uint64_t dv = umma_desc_mn_sw128(smem_u32(sKV + size_t(2 * stage + 1) * FA_TILE_BYTES), 0);
       if (more) wait_inputs(g + 1);
-      mbar_wait(&s_free[i], uint32_t(g & 1));
+      wait_bar(&s_free[i], uint32_t(g & 1));
       FA_TRACE(2 + i, g * 8 + 0);
       tc_fence_after();
       if (more) issue_qk(g + 1);          // next block's scores first: the softmax warps wait on these
       FA_TRACE(2 + i, g * 8 + 1);
-      mbar_wait(&p_full[i], uint32_t(g & 1));
+      wait_bar(&p_full[i], uint32_t(g & 1));
       FA_TRACE(2 + i, g * 8 + 2);
       tc_fence_after();
       if (elect_one()) {
@@ -242,6 +255,16 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
       if (i == 1 && total_g > 0) asm volatile("bar.arrive 1, 256;" ::: "memory");      // tile 0 goes first
     }
     int g = 0;
+    uint32_t r[4][32];       // one whole S row (128 scores)
+    bool pending = false;    // P of the previous block written but not yet signalled
+    if constexpr ((VAR & 128) != 0) {
+      if (total_g > 0) {
+        mbar_wait(&s_full[i], 0);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(t_s + uint32_t(c * 32), r[c]);
+      }
+    }
     for (int it = 0; it < my_items; ++it) {
       const int w = int(blockIdx.x) + it * int(gridDim.x);
       const int qb = w % p.q_blocks;
@@ -251,9 +274,24 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
       const int row = qb * (2 * FA_BQ) + i * FA_BQ + q * 32 + lane;   // query index within the utterance
       float m_used = -INFINITY;      // stale running maximum (raw score units)
       float l_run = 0.f;
-      bool pending = false;          // P of the previous block written but not yet signalled
 
       for (int j = 0; j < n_blocks; ++j, ++g) {
+        const int valid = p.kv_len - j * FA_BK;       // keys of this block that exist
+        if constexpr ((VAR & 128) != 0) {
+          // rolling prefetch: this block's scores were requested chunk by chunk under the previous block's
+          // exponentials (or by the prologue); P of the previous block is signalled together with the S hand-back
+          FA_TRACE(i, g * 8 + 0);
+          tmem_ld_wait();
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (pending) mbar_arrive(&p_full[i]);
+            mbar_arrive(&s_free[i]);
+          }
+          pending = false;
+          FA_TRACE(i, g * 8 + 1);
+        } else {
         FA_TRACE(i, g * 8 + 0);
         mbar_wait(&s_full[i], uint32_t(g & 1));
         FA_TRACE(i, g * 8 + 1);
@@ -264,8 +302,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
         // which keeps the live set at 128 scores + 16 packed probabilities.
         // (Tried and rejected, with measurements in DESIGN.md: two passes over TMEM with 64 live scores; a speculative
         // single pass against the stale maximum; 16 softmax warps with two threads per row.)
-        const int valid = p.kv_len - j * FA_BK;       // keys of this block that exist
-        uint32_t r[4][32];
         tmem_ld_32x32b_x32(t_s, r[0]);
         tmem_ld_32x32b_x32(t_s + 32, r[1]);
         if (pending) {
@@ -282,6 +318,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[i]);       // every read of S has landed: the next QK^T may overwrite it
+        }
         FA_TRACE(i, g * 8 + 3);
         if (valid < FA_BK) {
 #pragma unroll
@@ -291,13 +328,17 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
               if (c * 32 + e >= valid) r[c][e] = 0xff800000u;      // -inf
         }
         // four independent chains (a single chain of 64 dependent FMNMX3 costs ~400 cycles per block)
-        float mxc[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        float mxc[8] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
-          for (int e = 0; e < 32; ++e)
-            mxc[c] = fmaxf(mxc[c], __uint_as_float(r[c][e]));
-        const float mx = fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3]));
+          for (int e = 0; e < 32; ++e) {
+            constexpr int kHalf = (VAR & 256) ? 16 : 32;      // 8 chains: each chunk's halves reduce separately
+            const int ch = 2 * c + (e / kHalf) % 2;
+            mxc[ch] = fmaxf(mxc[ch], __uint_as_float(r[c][e]));
+          }
+        const float mx = fmaxf(fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3])),
+                               fmaxf(fmaxf(mxc[4], mxc[5]), fmaxf(mxc[6], mxc[7])));
         FA_TRACE(i, g * 8 + 2);
         const bool grow = mx > m_used + 5.545177f;     // 8 in log2 units; first block: m_used = -inf
         const bool any_grow = __any_sync(0xffffffffu, grow);
@@ -326,9 +367,17 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
           // so POLY of every 16 pairs are evaluated on the FMA pipe instead (exp2_poly2).
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
+            constexpr int kMuPairs = 64 - 4 * POLY;           // split phases: pairs [0, kMuPairs) on the MUFU
+            if constexpr ((VAR & 64) != 0) {
+              if (c * 16 + e == kMuPairs) {                   // MUFU phase over: the other tile's turn
+                if (i == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");
+                else if (g + 1 < total_g) asm volatile("bar.arrive 1, 256;" ::: "memory");
+              }
+            }
             const uint64_t t2 = f2_fma(f2_pack(__uint_as_float(r[c][2 * e]), __uint_as_float(r[c][2 * e + 1])), log2e2, negm2);
             float p0, p1;
-            if (((e * POLY) & 15) < POLY && POLY > 0) {       // evenly spread POLY of 16
+            const bool use_poly = (VAR & 64) ? (c * 16 + e >= kMuPairs) : (((e * POLY) & 15) < POLY && POLY > 0);
+            if (use_poly) {       // evenly spread POLY of 16 (split phases: the last 4 * POLY pairs)
               exp2_poly2(t2, p0, p1);
             } else {
               f2_unpack(t2, p0, p1);
@@ -365,7 +414,19 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
             }
           }
           tmem_st_32x32b_x16(t_p + uint32_t(c * 16), pk);
-          if constexpr ((VAR & 16) != 0) {
+          if constexpr ((VAR & 128) != 0) {
+            // chunk c's score registers are dead: refill them with the next block's scores (the next QK^T was issued
+            // when this block's S was handed back, a whole max + exp2 chunk ago)
+            if (g + 1 < total_g && c >= 1) {
+              if (c == 1) {
+                mbar_wait(&s_full[i], uint32_t((g + 1) & 1));
+                tc_fence_after();
+                tmem_ld_32x32b_x32(t_s, r[0]);
+              }
+              tmem_ld_32x32b_x32(t_s + uint32_t(c * 32), r[c]);
+            }
+          }
+          if constexpr ((VAR & 16) != 0 && ((VAR & 64) == 0 || POLY == 0)) {
             if (c == ((VAR & 32) ? 2 : 3)) {            // hand the turn over (bit 5: one chunk early)
               if (i == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");
               else if (g + 1 < total_g) asm volatile("bar.arrive 1, 256;" ::: "memory");
@@ -454,11 +515,16 @@ int launch_attention_tcgen05(const AttnDesc& d, cudaStream_t stream) {
   if ((rc = make_map(enc, &mq, d.q, d.heads, d.q_len, d.batch, d.ldq))) return rc;
   if ((rc = make_map(enc, &mk, d.k, d.heads, d.kv_len, d.batch, d.ldk))) return rc;
   if ((rc = make_map(enc, &mv, d.v, d.heads, d.kv_len, d.batch, d.ldv))) return rc;
+  // compiled variants (VAR, POLY); FA_VAR_SPLIT with 5 polynomial pairs of 16 is the default, the others are A/B knobs (TASTE_FA_VAR / TASTE_FA_POLY)
+#define FA_VARIANTS(X)                                                                                          \
+  X(FA_VAR_DEFAULT, FA_POLY) X(FA_VAR_DEFAULT, 0) X(FA_VAR_DEFAULT | 4, FA_POLY) X(0, FA_POLY)                  \
+  X(FA_VAR_SPLIT, 5) X(FA_VAR_SPLIT, 6) X(FA_VAR_SPLIT | 512, 5) X(FA_VAR_SPLIT | 128, 5)                      \
+  X(FA_VAR_SPLIT | 128 | 256, 5) X(FA_VAR_SPLIT | 128 | 512, 5) X(FA_VAR_SPLIT | 128 | 256 | 512, 5)           \
+  X(FA_VAR_SPLIT | 128 | 256 | 512, 6) X(FA_VAR_SPLIT | 128 | 256 | 512, 4) X(FA_VAR_DEFAULT | 128 | 256 | 512, FA_POLY)
   static bool configured = false;
   if (!configured) {
-#define FA_CFG(V, P) TASTE_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<V, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM))
-    FA_CFG(FA_VAR_DEFAULT, FA_POLY); FA_CFG(FA_VAR_DEFAULT, 0); FA_CFG(FA_VAR_DEFAULT | 4, FA_POLY);
-    FA_CFG(0, FA_POLY); FA_CFG(10, FA_POLY); FA_CFG(26, FA_POLY);
+#define FA_CFG(V, P) TASTE_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<(V), (P)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM));
+    FA_VARIANTS(FA_CFG)
 #undef FA_CFG
     configured = true;
   }
@@ -485,15 +551,19 @@ int launch_attention_tcgen05(const AttnDesc& d, cudaStream_t stream) {
   ProfScope ps(stream, d.kclass == KC_ATTN_ENC ? KC_ATTN_ENC : KC_ATTN_TC, 4.0 * pairs * FA_HD * d.heads,
                2.0 * FA_HD * d.heads * double(d.batch) * (2.0 * d.q_len + 2.0 * d.kv_len));
   const char* ep = getenv("TASTE_FA_POLY");          // A/B knob: "0" = every exponential on the MUFU
+  const int want_var = var >= 0 ? var : FA_VAR_SPLIT;
+  const int want_poly = ep ? atoi(ep) : ((want_var & 64) ? 5 : FA_POLY);
+  bool launched = false;
   // variants without register reallocation run 11 warps (no idle twelfth warp)
-#define FA_GO(V, P) attention_tcgen05_kernel<V, P><<<grid, ((V) & 2) ? FA_THREADS : FA_THREADS - 32, FA_SMEM, stream>>>(mq, mk, mv, p)
-  if (var == 4) FA_GO(FA_VAR_DEFAULT | 4, FA_POLY);        // timeline trace (scripts/attn_trace.py)
-  else if (var == 0) FA_GO(0, FA_POLY);                    // round-1 v7 scheduling: 168 registers, free-running tiles
-  else if (var == 10) FA_GO(10, FA_POLY);                  // + setmaxnreg 232 / 40
-  else if (var == 26) FA_GO(26, FA_POLY);                  // + strict ping-pong
-  else if (ep && atoi(ep) == 0) FA_GO(FA_VAR_DEFAULT, 0);
-  else FA_GO(FA_VAR_DEFAULT, FA_POLY);
+#define FA_GO(V, P)                                                                                                   \
+  if (!launched && want_var == (V) && want_poly == (P)) {                                                             \
+    attention_tcgen05_kernel<(V), (P)><<<grid, ((V) & 2) ? FA_THREADS : FA_THREADS - 32, FA_SMEM, stream>>>(mq, mk, mv, p); \
+    launched = true;                                                                                                  \
+  }
+  FA_VARIANTS(FA_GO)
 #undef FA_GO
+#undef FA_VARIANTS
+  if (!launched) return set_error(TASTE_E_ARG, "attention: variant %d / poly %d is not compiled", want_var, want_poly);
   TASTE_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -74,6 +74,30 @@ TASTE_DEVINL void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+// Long waits of single-purpose warps (an MMA issuer waiting for the softmax warps): try_wait with a suspend-time hint,
+// so the warp is parked by the hardware until the phase completes instead of re-polling every ~90 cycles, and a spin
+// body of four instructions (ncu, attention v9: the polling loops of the two MMA issuers and of the producer executed
+// 17 % of the kernel's instructions, on the schedulers they share with the softmax warps).
+TASTE_DEVINL void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(200000u)
+        : "memory");
+    if (ok) return;
+    if ((++spins & 0xFFu) == 0) {
+      const uint64_t t = global_timer_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > TASTE_WAIT_LIMIT_NS) __trap();
+    }
+  }
+}
 // One lane of a fully converged warp (warp-uniform control flow around it lets the compiler emit tcgen05 / TMA
 // instructions once, instead of a per-active-lane ELECT loop as inside an `if (lane == 0)` region).
 TASTE_DEVINL bool elect_one() {
