@@ -24,6 +24,23 @@ for mode in (0, 1):
                                  S, S, B, H, 0, st)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
+    if mode == 0 and os.environ.get("ATTN_CLOCKS"):
+        # SM clock and board power under a sustained run of this kernel alone (is the micro-benchmark power-capped?)
+        import pynvml, time
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(0)
+        e0.record()
+        for _ in range(400):
+            lib.taste_attention_bf16(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(o), 3 * D, 3 * D, 3 * D, D, None,
+                                     None, S, S, B, H, 0, st)
+        e1.record()
+        smp = []
+        while not e1.query():
+            smp.append((pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0))
+            time.sleep(0.02)
+        torch.cuda.synchronize()
+        print(f"sustained: {e0.elapsed_time(e1) / 400:.3f} ms/launch; clocks MHz {sorted(c for c, _ in smp)[len(smp) // 2]}"
+              f" (min {min(c for c, _ in smp)}, max {max(c for c, _ in smp)}), power W max {max(w for _, w in smp):.0f}", flush=True)
     print(f"mode {mode} ({'tcgen05' if mode == 0 else 'mma.sync'}): {ms:.3f} ms  {4.0*B*H*S*S*64/ms/1e9:.1f} TF/s", flush=True)
     outs.append(o.float().clone())
 lib.taste_attention_set_mode(0)

@@ -24,6 +24,8 @@
 // third.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -34,22 +36,20 @@ constexpr int FA_BK = 128;          // keys per block
 constexpr int FA_HD = 64;
 constexpr int FA_STAGES = 4;
 constexpr int FA_THREADS = 384;          // 12 warps: three full warpgroups (setmaxnreg is per warpgroup)
-#ifndef FA_POLY
-#define FA_POLY 6                   // of every 16 score pairs, this many take the polynomial exp2 path
-#endif
-// VAR bits: 2 = setmaxnreg (softmax warpgroups 216, others 64), 8 = 232 / 40 instead, 16 = ping-pong of the two
-// tiles' exp2 phases, 32 = hand the turn over one chunk early, 4 = timeline trace, 64 = split phases: the MUFU pairs
-// first (one tile's warp saturates the XU pipe), the turn is handed over, then the polynomial pairs (FMA pipe) run
-// under the other tile's MUFU phase, 128 = rolling prefetch: as soon as a 32-score chunk has been exponentiated its
-// registers are refilled with the NEXT block's scores (tcgen05.ld under the exponentials), so the s_full wait and the
-// TMEM load latency leave the per-tile serial loop, 256 = eight row-maximum chains instead of four, 512 = MMA issuers
-// wait parked (try_wait with a suspend hint) and the producer polls every ~1 us (their polling loops took issue slots
-// from the softmax warps on three of the four schedulers)
-constexpr int FA_VAR_DEFAULT = 2 | 8 | 16 | 32;
-constexpr int FA_VAR_SPLIT = FA_VAR_DEFAULT | 64;
+// VAR bits (template parameter; A/B knobs, see launch_attention_tcgen05): 4 = in-kernel timeline trace,
+// 64 = split phases: a row's MUFU pairs first, under the tile's ping-pong turn (one warp saturates the XU pipe), the
+// turn is handed over, then the polynomial pairs (FMA pipe) run under the other tile's MUFU phase; without it POLY of
+// every 16 pairs are interleaved and the turn is handed over after three of the four chunks,
+// 128 = speculative blocks: no row maximum after an item's first block (see the softmax loop), 256 = eight
+// row-maximum chains instead of four.
+constexpr int FA_VAR_INTERLEAVED = 0;
+constexpr int FA_VAR_SPLIT = 64;
+constexpr int FA_VAR_SPEC = 64 | 128;
 constexpr uint32_t FA_TILE_BYTES = FA_BQ * FA_HD * 2;      // 16 KB: one Q, K or V tile
 // Q is double buffered (2 x 2 tiles) so the next work item's queries load under the current item's last blocks
-constexpr size_t FA_SMEM = 1024 + size_t(4 + 2 * FA_STAGES) * FA_TILE_BYTES + 256;
+// + 8 x 4 KB output staging (one 32-row x 128-byte tile per softmax warp, TMA-stored): 230 656 B of the 232 448 available
+constexpr uint32_t FA_OUT_BYTES = 32 * FA_HD * 2;
+constexpr size_t FA_SMEM = 1024 + size_t(4 + 2 * FA_STAGES) * FA_TILE_BYTES + 8 * FA_OUT_BYTES + 256;
 
 // TMEM columns
 constexpr uint32_t FA_COL_S = 0;      // S0 [0,128)  S1 [128,256)
@@ -58,10 +58,38 @@ constexpr uint32_t FA_COL_P = 384;    // P0 [384,448) P1 [448,512)   (bf16 pairs
 
 struct FaParams {
   long long* dbg;      // timeline trace (VAR bit 2 only)
-  __nv_bfloat16* o;
-  int ldo;
   int q_len, kv_len;
   int heads, q_blocks, n_items;      // work item w = (b * heads + head) * q_blocks + qb
+};
+
+// Work item w = (b * heads + head) * q_blocks + qb, walked with stride gridDim.x.  The stride is decomposed once; each
+// step is three adds with carries (integer division runs on the XU pipe, behind the softmax warps' exponentials).
+struct FaItemWalk {
+  int qb, head, b;
+  int d_qb, d_head, d_b;
+  __device__ FaItemWalk(int first, int stride, int q_blocks, int heads) {
+    qb = first % q_blocks;
+    const int bh = first / q_blocks;
+    head = bh % heads;
+    b = bh / heads;
+    d_qb = stride % q_blocks;
+    const int dbh = stride / q_blocks;
+    d_head = dbh % heads;
+    d_b = dbh / heads;
+  }
+  __device__ void next(int q_blocks, int heads) {
+    qb += d_qb;
+    head += d_head;
+    b += d_b;
+    if (qb >= q_blocks) {
+      qb -= q_blocks;
+      ++head;
+    }
+    if (head >= heads) {
+      head -= heads;
+      ++b;
+    }
+  }
 };
 
 #define FA_TRACE(slot, idx)                                                      \
@@ -76,12 +104,14 @@ struct FaParams {
 template <int VAR, int POLY>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
-                         const __grid_constant__ CUtensorMap tma_v, const FaParams p) {
+                         const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_o,
+                         const FaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                   // 2 buffers x 2 tiles
   uint8_t* sKV = smem + 4 * FA_TILE_BYTES;              // FA_STAGES x {K, V}
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + size_t(2 * FA_STAGES) * FA_TILE_BYTES);
+  uint8_t* sOut = sKV + size_t(2 * FA_STAGES) * FA_TILE_BYTES;        // 8 warps x 4 KB (1024-byte aligned)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + 8 * FA_OUT_BYTES);
   uint64_t* q_full = bars;                              // [2]
   uint64_t* q_empty = bars + 2;                         // [2]  all QK^T of the item retired (MMA -> producer)
   uint64_t* kv_full = bars + 4;                         // [FA_STAGES]
@@ -102,6 +132,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
     tma_prefetch_desc(&tma_q);
     tma_prefetch_desc(&tma_k);
     tma_prefetch_desc(&tma_v);
+    tma_prefetch_desc(&tma_o);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&q_full[s], 1);
       mbar_init(&q_empty[s], 2);            // one tcgen05.commit per MMA issuer
@@ -129,11 +160,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
 
   // Producer and MMA warps run warp-uniform loops and elect one lane around the TMA / tcgen05 instructions (inside an
   // `if (lane == 0)` region every UTCHMMA is wrapped in an ELECT loop: ~90 cycles per MMA, measured with FA_TRACE).
-  // VAR bit 1: register reallocation between warpgroups (the softmax threads hold a whole 128-score row + the prefetched
-  // chunk of the next block; the TMA / MMA warps need almost nothing).  256 x 216 + 128 x 64 <= 384 x 168.
-  // (the instruction sits at the head of each role's branch: ptxas budgets registers per region it dominates)
-#define FA_REGS_SMALL() do { if constexpr ((VAR & 2) != 0) { if constexpr ((VAR & 8) != 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;"); else asm volatile("setmaxnreg.dec.sync.aligned.u32 64;"); } } while (0)
-#define FA_REGS_LARGE() do { if constexpr ((VAR & 2) != 0) { if constexpr ((VAR & 8) != 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;"); else asm volatile("setmaxnreg.inc.sync.aligned.u32 216;"); } } while (0)
+  // Register reallocation between warpgroups (setmaxnreg): the softmax threads hold a whole 128-score row and
+  // schedule their exp2 phase far better with 232 registers; the TMA / MMA warps need almost nothing.
+  // 256 x 232 + 128 x 40 <= 384 x 168.  (The instruction sits at the head of each role's branch: ptxas budgets
+  // registers per region it dominates.)
+#define FA_REGS_SMALL() asm volatile("setmaxnreg.dec.sync.aligned.u32 40;")
+#define FA_REGS_LARGE() asm volatile("setmaxnreg.inc.sync.aligned.u32 232;")
   if (warp == 11) {
     FA_REGS_SMALL();        // idle: only completes the third warpgroup
   } else if (warp == 8) {
@@ -141,16 +173,13 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
     FA_REGS_SMALL();
     int stage = 0;
     uint32_t phase = 0;
-    for (int it = 0; it < my_items; ++it) {
-      const int w = int(blockIdx.x) + it * int(gridDim.x);
-      const int qb = w % p.q_blocks;
-      const int bh = w / p.q_blocks;
-      const int head = bh % p.heads;
-      const int b = bh / p.heads;
-      const int q0 = qb * (2 * FA_BQ);
+    FaItemWalk walk(int(blockIdx.x), int(gridDim.x), p.q_blocks, p.heads);
+    for (int it = 0; it < my_items; ++it, walk.next(p.q_blocks, p.heads)) {
+      const int head = walk.head;
+      const int b = walk.b;
+      const int q0 = walk.qb * (2 * FA_BQ);
       const int qbuf = it & 1;
-      if constexpr ((VAR & 512) != 0) mbar_wait_parked(&q_empty[qbuf], uint32_t(((it >> 1) & 1) ^ 1));
-      else mbar_wait_relaxed(&q_empty[qbuf], uint32_t(((it >> 1) & 1) ^ 1));
+      mbar_wait_relaxed(&q_empty[qbuf], uint32_t(((it >> 1) & 1) ^ 1));
       if (elect_one()) {
         uint8_t* sq = sQ + size_t(2 * qbuf) * FA_TILE_BYTES;
         mbar_expect_tx(&q_full[qbuf], 2 * FA_TILE_BYTES);
@@ -159,8 +188,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
       }
       __syncwarp();
       for (int j = 0; j < n_blocks; ++j) {
-        if constexpr ((VAR & 512) != 0) mbar_wait_parked(&kv_empty[stage], phase ^ 1);
-        else mbar_wait_relaxed(&kv_empty[stage], phase ^ 1);
+        mbar_wait_relaxed(&kv_empty[stage], phase ^ 1);
         uint8_t* sk = sKV + size_t(2 * stage) * FA_TILE_BYTES;
         if (elect_one()) {
           mbar_expect_tx(&kv_full[stage], 2 * FA_TILE_BYTES);
@@ -182,12 +210,28 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
     const int i = warp - 9;
     constexpr uint32_t idesc_qk = umma_idesc(FA_BQ, FA_BK, 1, 0, 0);        // A, B K-major
     constexpr uint32_t idesc_pv = umma_idesc(FA_BQ, FA_HD, 1, 0, 1);        // A from TMEM, B (V) MN-major
-    // S_i = Q_i K^T for global block index g (item g / n_blocks, key block g % n_blocks)
-    auto issue_qk = [&](int g) {
-      const int qbuf = (g / n_blocks) & 1;
-      const int stage = g % FA_STAGES;
-      const uint64_t da = umma_desc_k_sw128(smem_u32(sQ + size_t(2 * qbuf + i) * FA_TILE_BYTES));
-      const uint64_t db = umma_desc_k_sw128(smem_u32(sKV + size_t(2 * stage) * FA_TILE_BYTES));
+    // No integer division in this loop: I2F / MUFU.RCP / F2I queue behind the softmax warps' exponentials on the XU
+    // pipe (in-kernel timeline: 600-700 cycles per loop step, which left the issuers with no slack at all), so the
+    // position of the block whose QK^T is issued next (one ahead of the block whose P V is issued) is carried along.
+    constexpr uint64_t kPairStep = (2 * FA_TILE_BYTES) >> 4;     // descriptor address units between Q buffers / stages
+    const uint64_t da_base = umma_desc_k_sw128(smem_u32(sQ + size_t(i) * FA_TILE_BYTES));
+    const uint64_t db_base = umma_desc_k_sw128(smem_u32(sKV));
+    const uint64_t dv_base = umma_desc_mn_sw128(smem_u32(sKV + FA_TILE_BYTES), 0);
+    int nj = 0, nit = 0, nstage = 0;            // next QK^T: key block within its item, item, K/V ring stage
+    uint32_t nphase = 0;
+    // everything that block needs from the producer: its K/V stage and, on the first block of an item, the item's Q
+    // (also waits for `also`, polled together with the K/V stage: a successful try_wait takes ~150 cycles to return)
+    auto wait_inputs_next = [&](uint64_t* also, uint32_t also_parity) {
+      const bool kv_ok = mbar_try_wait(&kv_full[nstage], nphase);
+      const bool also_ok = also == nullptr || mbar_try_wait(also, also_parity);
+      if (nj == 0) mbar_wait(&q_full[nit & 1], uint32_t((nit >> 1) & 1));
+      if (!kv_ok) mbar_wait(&kv_full[nstage], nphase);
+      if (!also_ok) mbar_wait(also, also_parity);
+      tc_fence_after();
+    };
+    auto issue_qk_next = [&]() {
+      const uint64_t da = da_base + uint64_t(nit & 1) * kPairStep;
+      const uint64_t db = db_base + uint64_t(nstage) * kPairStep;
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < FA_HD / 16; ++k)
@@ -196,39 +240,35 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
         umma_commit(&s_full[i]);
       }
       __syncwarp();
-    };
-    // everything block g needs from the producer: its K/V stage and, on the first block of an item, the item's Q
-    auto wait_bar = [&](uint64_t* bar, uint32_t parity) {
-      if constexpr ((VAR & 512) != 0) mbar_wait_parked(bar, parity);
-      else mbar_wait(bar, parity);
-    };
-    auto wait_inputs = [&](int g) {
-      const int it = g / n_blocks;
-      if (g % n_blocks == 0) wait_bar(&q_full[it & 1], uint32_t((it >> 1) & 1));
-      wait_bar(&kv_full[g % FA_STAGES], uint32_t((g / FA_STAGES) & 1));
-      tc_fence_after();
+      if (++nj == n_blocks) {
+        nj = 0;
+        ++nit;
+      }
+      if (++nstage == FA_STAGES) {
+        nstage = 0;
+        nphase ^= 1;
+      }
     };
     if (total_g > 0) {
-      wait_inputs(0);
+      wait_inputs_next(nullptr, 0);
       // tile 1 starts half a block behind tile 0 (when tile 0's first S tile has been read), so that one warpgroup
       // is in its exp2-heavy pass while the other reads / reduces scores instead of both hitting the MUFU together
-      if (i == 1) wait_bar(&s_free[0], 0);
-      issue_qk(0);
+      if (i == 1) mbar_wait(&s_free[0], 0);
+      issue_qk_next();
     }
+    int j = 0, stage = 0, qbuf = 0;             // the block whose P V is issued
     for (int g = 0; g < total_g; ++g) {
-      const int j = g % n_blocks;
-      const int stage = g % FA_STAGES;
       const bool more = g + 1 < total_g;
-      const uint64_t dv = umma_desc_mn_sw128(smem_u32(sKV + size_t(2 * stage + 1) * FA_TILE_BYTES), 0);
-      if (more) wait_inputs(g + 1);
-      wait_bar(&s_free[i], uint32_t(g & 1));
+      if (more) wait_inputs_next(&s_free[i], uint32_t(g & 1));
+      else mbar_wait(&s_free[i], uint32_t(g & 1));
       FA_TRACE(2 + i, g * 8 + 0);
       tc_fence_after();
-      if (more) issue_qk(g + 1);          // next block's scores first: the softmax warps wait on these
+      if (more) issue_qk_next();          // next block's scores first: the softmax warps wait on these
       FA_TRACE(2 + i, g * 8 + 1);
-      wait_bar(&p_full[i], uint32_t(g & 1));
+      mbar_wait(&p_full[i], uint32_t(g & 1));
       FA_TRACE(2 + i, g * 8 + 2);
       tc_fence_after();
+      const uint64_t dv = dv_base + uint64_t(stage) * kPairStep;
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < FA_BK / 16; ++k)     // 16 keys per MMA: 8 TMEM columns of P, 2048 B of V
@@ -236,10 +276,15 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
                   dv + uint64_t(k * (2048 >> 4)), idesc_pv, (j | k) != 0 ? 1u : 0u);
         umma_commit(&o_full[i]);
         umma_commit(&kv_empty[stage]);                                   // needs both tiles' commits
-        if (j == n_blocks - 1) umma_commit(&q_empty[(g / n_blocks) & 1]);   // likewise
+        if (j == n_blocks - 1) umma_commit(&q_empty[qbuf]);              // likewise
       }
       __syncwarp();
       FA_TRACE(2 + i, g * 8 + 3);
+      if (++j == n_blocks) {
+        j = 0;
+        qbuf ^= 1;
+      }
+      if (++stage == FA_STAGES) stage = 0;
     }
   } else {
     // ===================== softmax + output (warps 0-7) =====================
@@ -251,57 +296,79 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
     const uint32_t t_o = lane_base + FA_COL_O + uint32_t(i * FA_HD);
     const uint32_t t_p = lane_base + FA_COL_P + uint32_t(i * 64);
     const float kLog2e = 1.4426950408889634f;
-    if constexpr ((VAR & 16) != 0) {
-      if (i == 1 && total_g > 0) asm volatile("bar.arrive 1, 256;" ::: "memory");      // tile 0 goes first
-    }
+    constexpr bool kSplit = (VAR & 64) != 0;
+    constexpr bool kSpec = (VAR & 128) != 0;
+    constexpr int kMuPairs = 64 - 4 * POLY;         // split phases: pairs [0, kMuPairs) of a row on the MUFU
+    if (i == 1 && total_g > 0) asm volatile("bar.arrive 1, 256;" ::: "memory");      // tile 0 takes the first turn
     int g = 0;
-    uint32_t r[4][32];       // one whole S row (128 scores)
-    bool pending = false;    // P of the previous block written but not yet signalled
-    if constexpr ((VAR & 128) != 0) {
-      if (total_g > 0) {
-        mbar_wait(&s_full[i], 0);
-        tc_fence_after();
+    bool s_ready = false;            // early poll of s_full for the block about to start
+    // ---- output of a finished item: O_i / l (called once the item's last P V may be waited for; g = blocks done) ----
+    float out_inv = 0.f;
+    int out_head = 0, out_b = 0, out_row = 0, out_it = 0;
+    auto write_output = [&]() {
+      // Thread-per-row global stores (32 rows x 16 B per instruction) cost ~2 cycles per 16-byte request: 1900 cycles
+      // per item on the in-kernel timeline, 12 % of the kernel.  Each warp now stages its 32 x 64 bf16 tile in shared
+      // memory (128-byte swizzle: chunk ^ (row & 7), conflict-free 16-byte stores) and lane 0 hands it to the TMA,
+      // which also clips the rows past the utterance's last query.
+      mbar_wait(&o_full[i], uint32_t((g - 1) & 1));
+      FA_TRACE(4 + i, out_it * 8 + 0);
+      tc_fence_after();
+      const float inv = out_inv;
+      uint8_t* stage_out = sOut + size_t(warp) * FA_OUT_BYTES;
+      if (lane == 0) tma_store_wait_read();          // the previous item's store has read the staging tile
+      __syncwarp();
+      uint4* srow = reinterpret_cast<uint4*>(stage_out + lane * 128);
+      // (32 columns at a time: in the deferred call the next block's 128 scores are live as well)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(t_s + uint32_t(c * 32), r[c]);
+      for (int hc = 0; hc < 2; ++hc) {
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(t_o + uint32_t(hc * 32), o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o[8 * e + 0]) * inv, __uint_as_float(o[8 * e + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(o[8 * e + 2]) * inv, __uint_as_float(o[8 * e + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(o[8 * e + 4]) * inv, __uint_as_float(o[8 * e + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(o[8 * e + 6]) * inv, __uint_as_float(o[8 * e + 7]) * inv);
+          srow[(hc * 4 + e) ^ (lane & 7)] = u;
+        }
       }
-    }
-    for (int it = 0; it < my_items; ++it) {
-      const int w = int(blockIdx.x) + it * int(gridDim.x);
-      const int qb = w % p.q_blocks;
-      const int bh = w / p.q_blocks;
-      const int head = bh % p.heads;
-      const int b = bh / p.heads;
-      const int row = qb * (2 * FA_BQ) + i * FA_BQ + q * 32 + lane;   // query index within the utterance
+      tc_fence_before();      // O_i has been read: the next item's first P V (accumulate = 0) may overwrite it; that MMA
+                              // is issued only after this warpgroup's next p_full arrive, which follows in program order
+      FA_TRACE(4 + i, out_it * 8 + 2);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0 && out_row < p.q_len) {
+        tma_store_3d(&tma_o, stage_out, out_head * FA_HD, out_row, out_b);      // lane 0: `row` is the warp's first query
+        tma_store_commit();
+      }
+      FA_TRACE(4 + i, out_it * 8 + 3);
+    };
+    FaItemWalk walk(int(blockIdx.x), int(gridDim.x), p.q_blocks, p.heads);
+    for (int it = 0; it < my_items; ++it, walk.next(p.q_blocks, p.heads)) {
+      const int head = walk.head;
+      const int b = walk.b;
+      const int row = walk.qb * (2 * FA_BQ) + i * FA_BQ + q * 32 + lane;   // query index within the utterance
       float m_used = -INFINITY;      // stale running maximum (raw score units)
       float l_run = 0.f;
+      bool pending = false;          // P of the previous block written but not yet signalled
 
       for (int j = 0; j < n_blocks; ++j, ++g) {
-        const int valid = p.kv_len - j * FA_BK;       // keys of this block that exist
-        if constexpr ((VAR & 128) != 0) {
-          // rolling prefetch: this block's scores were requested chunk by chunk under the previous block's
-          // exponentials (or by the prologue); P of the previous block is signalled together with the S hand-back
-          FA_TRACE(i, g * 8 + 0);
-          tmem_ld_wait();
-          tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (pending) mbar_arrive(&p_full[i]);
-            mbar_arrive(&s_free[i]);
-          }
-          pending = false;
-          FA_TRACE(i, g * 8 + 1);
-        } else {
         FA_TRACE(i, g * 8 + 0);
-        mbar_wait(&s_full[i], uint32_t(g & 1));
+        // (a successful mbarrier.try_wait still takes ~150 cycles to return - in-kernel timeline - so the polls of
+        // barriers that are normally complete by the time they are needed are issued early and consumed here)
+        if (!s_ready) mbar_wait(&s_full[i], uint32_t(g & 1));
         FA_TRACE(i, g * 8 + 1);
         tc_fence_after();
         // The whole S row (128 fp32) is read into registers ONCE: one exposed TMEM latency per block, and the S tile
         // can be handed back to the MMA warp immediately, so the next block's QK^T runs under this block's entire
-        // softmax.  P goes back to TMEM in four 16-column stores as soon as each 32-score chunk is exponentiated,
-        // which keeps the live set at 128 scores + 16 packed probabilities.
-        // (Tried and rejected, with measurements in DESIGN.md: two passes over TMEM with 64 live scores; a speculative
-        // single pass against the stale maximum; 16 softmax warps with two threads per row.)
+        // softmax.  P goes back to TMEM in four 16-column stores as soon as each 32-score chunk is exponentiated.
+        // (Tried and rejected, with measurements in DESIGN.md: two passes over TMEM with 64 live scores; 16 softmax
+        // warps with two threads per row; refilling each chunk's registers with the next block's scores under the
+        // exponentials.)
+        const int valid = p.kv_len - j * FA_BK;       // keys of this block that exist
+        uint32_t r[4][32];
         tmem_ld_32x32b_x32(t_s, r[0]);
         tmem_ld_32x32b_x32(t_s + 32, r[1]);
         if (pending) {
@@ -318,124 +385,163 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[i]);       // every read of S has landed: the next QK^T may overwrite it
-        }
         FA_TRACE(i, g * 8 + 3);
         if (valid < FA_BK) {
 #pragma unroll
           for (int c = 0; c < 4; ++c)
+            if (valid < (c + 1) * 32) {               // warp-uniform: only the chunks that reach past the last key
 #pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (c * 32 + e >= valid) r[c][e] = 0xff800000u;      // -inf
+              for (int e = 0; e < 32; ++e)
+                if (c * 32 + e >= valid) r[c][e] = 0xff800000u;      // -inf
+            }
         }
-        // four independent chains (a single chain of 64 dependent FMNMX3 costs ~400 cycles per block)
-        float mxc[8] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        // Row maximum over the block: independent chains (a single chain of 64 dependent FMNMX3 costs ~400 cycles).
+        auto row_max = [&]() {
+          constexpr int kChains = (VAR & 256) ? 8 : 4;
+          float mxc[kChains];
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+          for (int c = 0; c < kChains; ++c) mxc[c] = -INFINITY;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            constexpr int kHalf = (VAR & 256) ? 16 : 32;      // 8 chains: each chunk's halves reduce separately
-            const int ch = 2 * c + (e / kHalf) % 2;
-            mxc[ch] = fmaxf(mxc[ch], __uint_as_float(r[c][e]));
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const int ch = (kChains == 8) ? 2 * c + e / 16 : c;
+              mxc[ch] = fmaxf(mxc[ch], __uint_as_float(r[c][e]));
+            }
+          float mx = fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3]));
+          if constexpr (kChains == 8) mx = fmaxf(mx, fmaxf(fmaxf(mxc[4], mxc[5]), fmaxf(mxc[6], mxc[7])));
+          return mx;
+        };
+        // Lazy rescale: the running reference m_used moves only when the block maximum exceeds it by more than 2^8
+        // (returns the factor for l_run and O; 1 for rows that keep their reference).
+        auto adopt_max = [&](float mx, bool& any_grow) {
+          const bool grow = mx > m_used + 5.545177f;     // 8 in log2 units; first block: m_used = -inf
+          any_grow = __any_sync(0xffffffffu, grow);
+          float alpha = 1.0f;
+          if (any_grow) {
+            const float m_new = grow ? mx : m_used;
+            alpha = (m_used == -INFINITY) ? 0.f : fast_exp2((m_used - m_new) * kLog2e);
+            l_run *= alpha;
+            m_used = m_new;
           }
-        const float mx = fmaxf(fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3])),
-                               fmaxf(fmaxf(mxc[4], mxc[5]), fmaxf(mxc[6], mxc[7])));
-        FA_TRACE(i, g * 8 + 2);
-        const bool grow = mx > m_used + 5.545177f;     // 8 in log2 units; first block: m_used = -inf
-        const bool any_grow = __any_sync(0xffffffffu, grow);
-        float alpha = 1.0f;
-        if (any_grow) {
-          const float m_new = grow ? mx : m_used;
-          alpha = (m_used == -INFINITY) ? 0.f : fast_exp2((m_used - m_new) * kLog2e);
-          l_run *= alpha;
-          m_used = m_new;
-        }
-        const float neg_m = -m_used * kLog2e;
-        const uint64_t negm2 = f2_pack(neg_m, neg_m);
-        const uint64_t log2e2 = f2_pack(kLog2e, kLog2e);
-        uint64_t sum2 = f2_pack(0.f, 0.f);
-        // VAR bit 4: ping-pong.  The two tiles' exp2 phases alternate (named barriers 1 / 2, FA3-style) instead of
-        // drifting into lock-step, where both warps of a scheduler fight for the MUFU queue and neither feeds the FMA
-        // pipe; the other tile's TMEM loads, row maximum and waits run under this tile's exponentials.
-        if constexpr ((VAR & 16) != 0) {
-          if (i == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
-          else asm volatile("bar.sync 2, 256;" ::: "memory");
-        }
+          return alpha;
+        };
+        auto rescale_o = [&](float alpha) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t pk[16];
-          // Exponentials in pairs (packed FFMA2 / FADD2).  16/clk/SM of MUFU.EX2 would cap the tensor pipe at 50 %,
-          // so POLY of every 16 pairs are evaluated on the FMA pipe instead (exp2_poly2).
+          for (int cc = 0; cc < FA_HD / 16; ++cc) {
+            uint32_t o[16];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
+                "%13, %14, %15}, [%16];"
+                : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]),
+                  "=r"(o[8]), "=r"(o[9]), "=r"(o[10]), "=r"(o[11]), "=r"(o[12]), "=r"(o[13]), "=r"(o[14]),
+                  "=r"(o[15])
+                : "r"(t_o + uint32_t(cc * 16))
+                : "memory");
+            tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            constexpr int kMuPairs = 64 - 4 * POLY;           // split phases: pairs [0, kMuPairs) on the MUFU
-            if constexpr ((VAR & 64) != 0) {
-              if (c * 16 + e == kMuPairs) {                   // MUFU phase over: the other tile's turn
+            for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+            tmem_st_32x32b_x16(t_o + uint32_t(cc * 16), o);
+          }
+        };
+        // One pass over the row: p = 2^(s * log2e - m_used * log2e), P (bf16) to TMEM chunk by chunk, returns the row
+        // sum.  Exponentials in pairs (packed FFMA2 / FADD2).  16/clk/SM of MUFU.EX2 alone would cap the tensor pipe
+        // at 50 %, so POLY of every 16 pairs are evaluated on the FMA pipe instead (degree-3 polynomial).
+        // kTurn: this is the tile's regular pass, taken under the ping-pong turn (see below); the redo pass of the
+        // speculative mode runs outside the protocol.
+        auto exp_pass = [&](auto turn_tag, bool rescale, float alpha) {
+          constexpr bool kTurn = decltype(turn_tag)::value;
+          bool o_ready = false;
+          if (kTurn && j > 0) o_ready = mbar_try_wait(&o_full[i], uint32_t((g - 1) & 1));      // consumed after chunk 0
+          const float neg_m = -m_used * kLog2e;
+          const uint64_t negm2 = f2_pack(neg_m, neg_m);
+          const uint64_t log2e2 = f2_pack(kLog2e, kLog2e);
+          const float c1 = kLog2e * (1.0f / 252.0f);                 // exp2_poly2_sat: t' = (t + 126) / 252
+          const float c0 = (126.0f + neg_m) * (1.0f / 252.0f);
+          uint64_t sum2 = f2_pack(0.f, 0.f);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t pk[16];
+            if (kTurn && c == 3) s_ready = (g + 1 < total_g) && mbar_try_wait(&s_full[i], uint32_t((g + 1) & 1));
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              if constexpr (kTurn && kSplit && POLY > 0) {
+                if (c * 16 + e == kMuPairs) {                   // MUFU phase over: the other tile's turn
+                  if (i == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");
+                  else if (g + 1 < total_g) asm volatile("bar.arrive 1, 256;" ::: "memory");
+                }
+              }
+              // split phases: the last 4 * POLY pairs of the row; otherwise POLY of every 16, evenly spread
+              const bool use_poly = POLY > 0 && (kSplit ? (c * 16 + e >= kMuPairs) : (((e * POLY) & 15) < POLY));
+              float p0, p1;
+              if (use_poly && kSpec) {
+                exp2_poly2_sat(__uint_as_float(r[c][2 * e]), __uint_as_float(r[c][2 * e + 1]), c1, c0, p0, p1);
+              } else {
+                const uint64_t t2 = f2_fma(f2_pack(__uint_as_float(r[c][2 * e]), __uint_as_float(r[c][2 * e + 1])), log2e2, negm2);
+                if (use_poly) {
+                  exp2_poly2(t2, p0, p1);
+                } else {
+                  f2_unpack(t2, p0, p1);
+                  p0 = fast_exp2(p0);
+                  p1 = fast_exp2(p1);
+                }
+              }
+              sum2 = f2_add(sum2, f2_pack(p0, p1));
+              pk[e] = pack_bf16x2(p0, p1);
+            }
+            if (kTurn && c == 0 && j > 0) {
+              // Only now is the previous block's P V needed: P_i has been consumed (it may be overwritten) and O_i is
+              // stable (it may be rescaled).  On the first block of an item the output pass below already waited.
+              FA_TRACE(i, g * 8 + 4);
+              if (!o_ready) mbar_wait(&o_full[i], uint32_t((g - 1) & 1));
+              FA_TRACE(i, g * 8 + 5);
+              tc_fence_after();
+              if (rescale) rescale_o(alpha);
+            }
+            tmem_st_32x32b_x16(t_p + uint32_t(c * 16), pk);
+            if constexpr (kTurn && !(kSplit && POLY > 0)) {
+              if (c == 2) {                                     // hand the turn over one chunk early
                 if (i == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");
                 else if (g + 1 < total_g) asm volatile("bar.arrive 1, 256;" ::: "memory");
               }
             }
-            const uint64_t t2 = f2_fma(f2_pack(__uint_as_float(r[c][2 * e]), __uint_as_float(r[c][2 * e + 1])), log2e2, negm2);
-            float p0, p1;
-            const bool use_poly = (VAR & 64) ? (c * 16 + e >= kMuPairs) : (((e * POLY) & 15) < POLY && POLY > 0);
-            if (use_poly) {       // evenly spread POLY of 16 (split phases: the last 4 * POLY pairs)
-              exp2_poly2(t2, p0, p1);
-            } else {
-              f2_unpack(t2, p0, p1);
-              p0 = fast_exp2(p0);
-              p1 = fast_exp2(p1);
-            }
-            sum2 = f2_add(sum2, f2_pack(p0, p1));
-            pk[e] = pack_bf16x2(p0, p1);
           }
-          if (c == 0 && j > 0) {
-            // Only now is the previous block's P V needed: P_i has been consumed (it may be overwritten) and O_i is
-            // stable (it may be rescaled).  On the first block of an item the output pass below already waited.
-            FA_TRACE(i, g * 8 + 4);
-            mbar_wait(&o_full[i], uint32_t((g - 1) & 1));
-            FA_TRACE(i, g * 8 + 5);
-            tc_fence_after();
-            if (any_grow) {
-#pragma unroll
-              for (int cc = 0; cc < FA_HD / 16; ++cc) {
-                uint32_t o[16];
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
-                    "%13, %14, %15}, [%16];"
-                    : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]),
-                      "=r"(o[8]), "=r"(o[9]), "=r"(o[10]), "=r"(o[11]), "=r"(o[12]), "=r"(o[13]), "=r"(o[14]),
-                      "=r"(o[15])
-                    : "r"(t_o + uint32_t(cc * 16))
-                    : "memory");
-                tmem_ld_wait();
-#pragma unroll
-                for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-                tmem_st_32x32b_x16(t_o + uint32_t(cc * 16), o);
-              }
-            }
-          }
-          tmem_st_32x32b_x16(t_p + uint32_t(c * 16), pk);
-          if constexpr ((VAR & 128) != 0) {
-            // chunk c's score registers are dead: refill them with the next block's scores (the next QK^T was issued
-            // when this block's S was handed back, a whole max + exp2 chunk ago)
-            if (g + 1 < total_g && c >= 1) {
-              if (c == 1) {
-                mbar_wait(&s_full[i], uint32_t((g + 1) & 1));
-                tc_fence_after();
-                tmem_ld_32x32b_x32(t_s, r[0]);
-              }
-              tmem_ld_32x32b_x32(t_s + uint32_t(c * 32), r[c]);
-            }
-          }
-          if constexpr ((VAR & 16) != 0 && ((VAR & 64) == 0 || POLY == 0)) {
-            if (c == ((VAR & 32) ? 2 : 3)) {            // hand the turn over (bit 5: one chunk early)
-              if (i == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");
-              else if (g + 1 < total_g) asm volatile("bar.arrive 1, 256;" ::: "memory");
+          float sum0, sum1;
+          f2_unpack(sum2, sum0, sum1);
+          return sum0 + sum1;
+        };
+
+        // Speculative mode (VAR bit 7): only the first block of an item computes its row maximum.  Later blocks
+        // exponentiate against the stale reference straight away - fp32 / bf16 carry 2^(+-126), so a reference that
+        // is too low costs no accuracy - and a row whose block sum shows that an argument came near the fp32 range
+        // (any p >= 2^100; the polynomial path clamps at 2^126 instead of wrapping) takes the exact path afterwards:
+        // maximum, rescale, second pass.  This removes ~80 of ~800 issue slots per block and the maximum -> exp2
+        // dependency from the per-tile serial loop.
+        const bool exact = !kSpec || j == 0;
+        bool any_grow = false;
+        float alpha = 1.0f;
+        if (exact) {
+          const float mx = row_max();
+          FA_TRACE(i, g * 8 + 2);
+          alpha = adopt_max(mx, any_grow);
+        }
+        // Ping-pong: the two tiles' exp2 phases alternate (named barriers 1 / 2, FA3-style) instead of drifting into
+        // lock-step, where both warps of a scheduler fight for the MUFU queue and neither feeds the FMA pipe; the other
+        // tile's TMEM loads, row maximum and waits run under this tile's exponentials.
+        if (i == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+        else asm volatile("bar.sync 2, 256;" ::: "memory");
+        float bsum = exp_pass(std::true_type{}, any_grow, alpha);
+        if constexpr (kSpec) {
+          if (!exact) {
+            const bool bad = !(bsum < 1.0e30f);            // also catches inf and NaN
+            if (__any_sync(0xffffffffu, bad)) {
+              alpha = adopt_max(row_max(), any_grow);
+              rescale_o(alpha);                            // o_full of the previous block was waited for in the pass
+              bsum = exp_pass(std::false_type{}, false, 1.0f);
             }
           }
         }
-        float sum0, sum1;
-        f2_unpack(sum2, sum0, sum1);
-        l_run += sum0 + sum1;
+        l_run += bsum;
         if (j + 1 < n_blocks) {
           pending = true;              // the P stores are waited for (and p_full signalled) under the next block's loads
         } else {
@@ -447,32 +553,17 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
         FA_TRACE(i, g * 8 + 6);
       }
 
-      // ---- output: O_i / l ----
-      mbar_wait(&o_full[i], uint32_t((g - 1) & 1));
-      tc_fence_after();
-      const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-      __nv_bfloat16* orow = p.o + (int64_t(b) * p.q_len + row) * p.ldo + head * FA_HD;
-#pragma unroll
-      for (int c = 0; c < FA_HD / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_o + uint32_t(c * 32), r);
-        tmem_ld_wait();
-        if (row < p.q_len) {
-          uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(r[8 * e + 0]) * inv, __uint_as_float(r[8 * e + 1]) * inv);
-            u.y = pack_bf16x2(__uint_as_float(r[8 * e + 2]) * inv, __uint_as_float(r[8 * e + 3]) * inv);
-            u.z = pack_bf16x2(__uint_as_float(r[8 * e + 4]) * inv, __uint_as_float(r[8 * e + 5]) * inv);
-            u.w = pack_bf16x2(__uint_as_float(r[8 * e + 6]) * inv, __uint_as_float(r[8 * e + 7]) * inv);
-            dst[e] = u;
-          }
-        }
-      }
-      tc_fence_before();      // O_i has been read: the next item's first P V (accumulate = 0) may overwrite it; that MMA
-                              // is issued only after this warpgroup's next p_full arrive, which follows in program order
+      // (Deferring this pass into the next item's first block, under its loads and row maximum, hides the wait for the
+      // last P V but costs more than it saves: with the extra live ranges in the block loop ptxas schedules the whole
+      // loop worse - measured 1.17 ms against 1.01 ms per layer.)
+      out_inv = l_run > 0.f ? __fdividef(1.0f, l_run) : 0.f;
+      out_head = head;
+      out_b = b;
+      out_row = row;
+      out_it = it;
+      write_output();
     }
+    if (lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -483,10 +574,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
 // host side
 // ------------------------------------------------------------------------------------------------
 // {64 * heads columns, rows, batch} view of a [batch * rows, ld] bf16 activation; box = 64 x 128 x 1
-static int make_map(EncodeTiledFn enc, CUtensorMap* m, const void* base, int heads, int rows, int batch, int ld) {
+static int make_map(EncodeTiledFn enc, CUtensorMap* m, const void* base, int heads, int rows, int batch, int ld,
+                    int box_rows = FA_BQ) {
   cuuint64_t dims[3] = {(cuuint64_t)heads * FA_HD, (cuuint64_t)rows, (cuuint64_t)batch};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)rows};
-  cuuint32_t box[3] = {FA_HD, FA_BQ, 1};
+  cuuint32_t box[3] = {FA_HD, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -501,7 +593,8 @@ extern "C" void taste_dbg_attention_trace(void* dev_buf) { g_fa_trace = static_c
 bool attention_tcgen05_eligible(const AttnDesc& d) {
   if (d.cu_q || d.cu_kv || d.causal) return false;
   if (d.q_len < 2 * FA_BQ || d.kv_len < FA_BK) return false;           // small problems: the mma.sync kernel
-  if ((reinterpret_cast<uintptr_t>(d.q) | reinterpret_cast<uintptr_t>(d.k) | reinterpret_cast<uintptr_t>(d.v)) & 15)
+  if ((reinterpret_cast<uintptr_t>(d.q) | reinterpret_cast<uintptr_t>(d.k) | reinterpret_cast<uintptr_t>(d.v) |
+       reinterpret_cast<uintptr_t>(d.o)) & 15)
     return false;
   if ((d.ldq | d.ldk | d.ldv | d.ldo) % 8 != 0) return false;
   return true;
@@ -510,17 +603,16 @@ bool attention_tcgen05_eligible(const AttnDesc& d) {
 int launch_attention_tcgen05(const AttnDesc& d, cudaStream_t stream) {
   EncodeTiledFn enc = get_tensor_map_encoder();
   if (!enc) return set_error(TASTE_E_NO_DEVICE, "cuTensorMapEncodeTiled entry point unavailable");
-  CUtensorMap mq, mk, mv;
+  CUtensorMap mq, mk, mv, mo;
   int rc;
   if ((rc = make_map(enc, &mq, d.q, d.heads, d.q_len, d.batch, d.ldq))) return rc;
   if ((rc = make_map(enc, &mk, d.k, d.heads, d.kv_len, d.batch, d.ldk))) return rc;
   if ((rc = make_map(enc, &mv, d.v, d.heads, d.kv_len, d.batch, d.ldv))) return rc;
+  if ((rc = make_map(enc, &mo, d.o, d.heads, d.q_len, d.batch, d.ldo, 32))) return rc;      // one warp's rows per store
   // compiled variants (VAR, POLY); FA_VAR_SPLIT with 5 polynomial pairs of 16 is the default, the others are A/B knobs (TASTE_FA_VAR / TASTE_FA_POLY)
 #define FA_VARIANTS(X)                                                                                          \
-  X(FA_VAR_DEFAULT, FA_POLY) X(FA_VAR_DEFAULT, 0) X(FA_VAR_DEFAULT | 4, FA_POLY) X(0, FA_POLY)                  \
-  X(FA_VAR_SPLIT, 5) X(FA_VAR_SPLIT, 6) X(FA_VAR_SPLIT | 512, 5) X(FA_VAR_SPLIT | 128, 5)                      \
-  X(FA_VAR_SPLIT | 128 | 256, 5) X(FA_VAR_SPLIT | 128 | 512, 5) X(FA_VAR_SPLIT | 128 | 256 | 512, 5)           \
-  X(FA_VAR_SPLIT | 128 | 256 | 512, 6) X(FA_VAR_SPLIT | 128 | 256 | 512, 4) X(FA_VAR_DEFAULT | 128 | 256 | 512, FA_POLY)
+  X(FA_VAR_SPLIT, 5) X(FA_VAR_SPLIT, 6) X(FA_VAR_SPLIT | 4, 5) X(FA_VAR_SPLIT | 256, 5)                        \
+  X(FA_VAR_INTERLEAVED, 6) X(FA_VAR_INTERLEAVED, 0) X(FA_VAR_SPEC, 5) X(FA_VAR_SPEC | 4, 5)
   static bool configured = false;
   if (!configured) {
 #define FA_CFG(V, P) TASTE_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<(V), (P)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM));
@@ -532,8 +624,6 @@ int launch_attention_tcgen05(const AttnDesc& d, cudaStream_t stream) {
   const int var = ev ? atoi(ev) : -1;
   FaParams p;
   p.dbg = g_fa_trace;
-  p.o = static_cast<__nv_bfloat16*>(d.o);
-  p.ldo = d.ldo;
   p.q_len = d.q_len;
   p.kv_len = d.kv_len;
   p.heads = d.heads;
@@ -552,12 +642,11 @@ int launch_attention_tcgen05(const AttnDesc& d, cudaStream_t stream) {
                2.0 * FA_HD * d.heads * double(d.batch) * (2.0 * d.q_len + 2.0 * d.kv_len));
   const char* ep = getenv("TASTE_FA_POLY");          // A/B knob: "0" = every exponential on the MUFU
   const int want_var = var >= 0 ? var : FA_VAR_SPLIT;
-  const int want_poly = ep ? atoi(ep) : ((want_var & 64) ? 5 : FA_POLY);
+  const int want_poly = ep ? atoi(ep) : ((want_var & 64) ? 5 : 6);
   bool launched = false;
-  // variants without register reallocation run 11 warps (no idle twelfth warp)
 #define FA_GO(V, P)                                                                                                   \
   if (!launched && want_var == (V) && want_poly == (P)) {                                                             \
-    attention_tcgen05_kernel<(V), (P)><<<grid, ((V) & 2) ? FA_THREADS : FA_THREADS - 32, FA_SMEM, stream>>>(mq, mk, mv, p); \
+    attention_tcgen05_kernel<(V), (P)><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, mo, p);                         \
     launched = true;                                                                                                  \
   }
   FA_VARIANTS(FA_GO)

@@ -74,30 +74,6 @@ TASTE_DEVINL void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
     }
   }
 }
-// Long waits of single-purpose warps (an MMA issuer waiting for the softmax warps): try_wait with a suspend-time hint,
-// so the warp is parked by the hardware until the phase completes instead of re-polling every ~90 cycles, and a spin
-// body of four instructions (ncu, attention v9: the polling loops of the two MMA issuers and of the producer executed
-// 17 % of the kernel's instructions, on the schedulers they share with the softmax warps).
-TASTE_DEVINL void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  uint64_t t0 = 0;
-  for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(200000u)
-        : "memory");
-    if (ok) return;
-    if ((++spins & 0xFFu) == 0) {
-      const uint64_t t = global_timer_ns();
-      if (t0 == 0) t0 = t;
-      else if (t - t0 > TASTE_WAIT_LIMIT_NS) __trap();
-    }
-  }
-}
 // One lane of a fully converged warp (warp-uniform control flow around it lets the compiler emit tcgen05 / TMA
 // instructions once, instead of a per-active-lane ELECT loop as inside an `if (lane == 0)` region).
 TASTE_DEVINL bool elect_one() {
@@ -137,6 +113,18 @@ TASTE_DEVINL void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* ba
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+
+// TMA store (shared -> global, bulk async-group completion).  The issuing thread commits a group per store and waits
+// for the reads of its earlier groups before the staging buffer is rewritten; out-of-range box rows are clipped.
+TASTE_DEVINL void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+TASTE_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+TASTE_DEVINL void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+TASTE_DEVINL void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
@@ -414,6 +402,31 @@ TASTE_DEVINL void exp2_poly2(uint64_t t2, float& p0, float& p1) {
   const uint64_t u = f2_add(t, magic);                        // low mantissa bits = round(t)
   const uint64_t n = f2_add(u, nmagic);
   const uint64_t f = f2_fma(n, f2_pack(-1.0f, -1.0f), t);     // t - n  in [-0.5, 0.5]
+  uint64_t p = f2_fma(f, f2_pack(5.517166712e-02f, 5.517166712e-02f), f2_pack(2.426111220e-01f, 2.426111220e-01f));
+  p = f2_fma(p, f, f2_pack(6.932609858e-01f, 6.932609858e-01f));
+  p = f2_fma(p, f, f2_pack(9.999280736e-01f, 9.999280736e-01f));
+  float q0, q1, u0, u1;
+  f2_unpack(p, q0, q1);
+  f2_unpack(u, u0, u1);
+  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(u0) << 23));
+  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(u1) << 23));
+}
+
+// Same polynomial, fed with raw scores: 2^(s * log2e - m) with the argument clamped on BOTH sides at no extra cost.
+// t' = sat(s * c1 + c0) with c1 = log2e / 252, c0 = (126 - m) / 252 maps t = s * log2e - m from [-126, 126] onto [0, 1]
+// (FFMA.SAT; -inf and NaN give 0), u = 252 t' - 126 + magic rounds t to the nearest integer n in the low mantissa bits,
+// f = 252 t' - 126 - n.  Ten instructions per pair, as exp2_poly2 + its scale FFMA2.  The upper clamp makes an argument
+// beyond the fp32 range produce >= 2^125 instead of a wrapped exponent, so the caller can detect it in the row sum.
+TASTE_DEVINL void exp2_poly2_sat(float s0, float s1, float c1, float c0, float& p0, float& p1) {
+  float a0, a1;
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(a0) : "f"(s0), "f"(c1), "f"(c0));
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(a1) : "f"(s1), "f"(c1), "f"(c0));
+  const uint64_t a = f2_pack(a0, a1);
+  const uint64_t k252 = f2_pack(252.0f, 252.0f);
+  const uint64_t mg = f2_pack(12582786.0f, 12582786.0f);                 // 1.5 * 2^23 - 126
+  const uint64_t u = f2_fma(a, k252, mg);                                // low mantissa bits = round(t)
+  const uint64_t nb = f2_fma(u, f2_pack(-1.0f, -1.0f), mg);              // -(n + 126), exact
+  const uint64_t f = f2_fma(a, k252, nb);                                // t - n  in [-0.5, 0.5]
   uint64_t p = f2_fma(f, f2_pack(5.517166712e-02f, 5.517166712e-02f), f2_pack(2.426111220e-01f, 2.426111220e-01f));
   p = f2_fma(p, f, f2_pack(6.932609858e-01f, 6.932609858e-01f));
   p = f2_fma(p, f, f2_pack(9.999280736e-01f, 9.999280736e-01f));

@@ -198,6 +198,53 @@ def test_attention_fixed(lib, B, S, H, mode):
     assert _rel(o.float(), ref) < 6e-3          # bf16 P and bf16 output rounding
 
 
+@pytest.mark.parametrize("variant", [None, (64, 6), (320, 5), (192, 5), (0, 6), (0, 0)])
+@pytest.mark.parametrize("jump", [0.0, 30.0, 250.0])
+def test_attention_score_range(lib, variant, jump, monkeypatch):
+    """Encoder kernel variants (TASTE_FA_VAR / TASTE_FA_POLY) on rows whose scores GROW along the key axis: later key
+    blocks exceed the running maximum by `jump` natural units.  30 stays inside the fp32 range of the stale-reference
+    exponentials; 250 overflows it and must take the exact path (maximum, rescale, second pass).  Some queries also
+    see strongly negative scores (argument clamp of the polynomial exp2)."""
+    if variant is not None:
+        monkeypatch.setenv("TASTE_FA_VAR", str(variant[0]))
+        monkeypatch.setenv("TASTE_FA_POLY", str(variant[1]))
+    else:
+        monkeypatch.delenv("TASTE_FA_VAR", raising=False)
+        monkeypatch.delenv("TASTE_FA_POLY", raising=False)
+    torch.manual_seed(11)
+    B, S, H = 2, 1500, 2
+    D = H * 64
+    qkv = (torch.randn(B * S, 3 * D, device="cuda") * 0.7)
+    q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+    # a shared direction: score offset = qa * kb[key]; kb steps up across the 128-key blocks
+    pos = torch.arange(S, device="cuda").repeat(B)
+    step = torch.zeros(B * S, device="cuda")
+    step[pos >= 300] = 0.2
+    step[pos >= 700] = 0.5
+    step[pos >= 1100] = 1.0
+    step[pos >= 1400] = 0.6                   # and down again: the last block must not dominate
+    qa = torch.full((B * S,), 4.0, device="cuda")
+    qa[::7] = -4.0                            # these queries prefer the EARLY keys (later scores strongly negative)
+    for h in range(H):
+        q[:, h * 64] = qa
+        k[:, h * 64] = step * (jump / 4.0)
+    qkv = qkv.bfloat16()
+    q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+    o = torch.full((B * S, D), float("nan"), device="cuda").bfloat16()
+    assert lib.taste_attention_set_mode(0) == 0
+    _lib.check(lib.taste_attention_bf16(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(o), 3 * D, 3 * D, 3 * D, D,
+                                        None, None, S, S, B, H, 0, _stream()), "attn")
+    torch.cuda.synchronize()
+    qh = q.float().view(B, S, H, 64).transpose(1, 2)
+    kh = k.float().view(B, S, H, 64).transpose(1, 2)
+    vh = v.float().view(B, S, H, 64).transpose(1, 2)
+    ref = _attn_ref(qh, kh, vh, False).transpose(1, 2).reshape(B * S, D)
+    assert torch.isfinite(o.float()).all()
+    assert _rel(o.float(), ref) < 6e-3
+    row_err = (o.float() - ref).norm(dim=1) / ref.norm(dim=1).clamp_min(1e-6)
+    assert float(row_err.max()) < 3e-2, int(row_err.argmax())       # no single row may be off (a missed rescale)
+
+
 @pytest.mark.parametrize("causal", [0, 1])
 def test_attention_ragged(lib, causal):
     torch.manual_seed(5 + causal)
