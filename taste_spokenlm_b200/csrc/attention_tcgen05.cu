@@ -22,6 +22,7 @@
 // The two tiles' exp2 phases are ping-ponged with named barriers: left alone they drift into lock-step (measured with
 // the in-kernel timeline), where both warps of a scheduler stall on the MUFU queue and the block period grows by a
 // third.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <type_traits>
@@ -31,11 +32,29 @@
 
 namespace taste {
 
-constexpr int FA_BQ = 128;          // query rows per tile (2 tiles per work item)
-constexpr int FA_BK = 128;          // keys per block
+constexpr int FA_BQ = 128;          // query rows per tile
 constexpr int FA_HD = 64;
-constexpr int FA_STAGES = 4;
-constexpr int FA_THREADS = 384;          // 12 warps: three full warpgroups (setmaxnreg is per warpgroup)
+// Geometry (template parameters NT, BK): NT query tiles of 128 rows per work item, each with its own softmax warpgroup
+// and MMA-issuing warp, walking over key blocks of BK keys.
+//   2 x 128: one thread holds a 128-score row (232 registers after setmaxnreg), two softmax warps per scheduler
+//   3 x 64 : 64-score rows (152 registers), three softmax warps per scheduler to hide each other's latencies
+template <int NT, int BK>
+struct FaCfg {
+  static constexpr int kThreads = NT * 128 + 128;       // softmax warpgroups + {TMA, NT MMA issuers, idle} warpgroup
+  static constexpr int kStages = 4;                     // K/V ring (a fifth 64-key stage fits but does not help)
+  static constexpr uint32_t kQTile = FA_BQ * FA_HD * 2;      // 16 KB
+  static constexpr uint32_t kKvTile = BK * FA_HD * 2;        // one K or V block
+  static constexpr uint32_t kOutBytes = 32 * FA_HD * 2;      // one warp's 32-row output tile
+  // Q is double buffered (2 x NT tiles) so the next work item's queries load under the current item's last blocks;
+  // + one 4 KB output staging tile per softmax warp (TMA-stored).  2 x 128: 230 656 B of the 232 448 available.
+  static constexpr size_t kSmem = 1024 + size_t(2 * NT) * kQTile + size_t(2 * kStages) * kKvTile + size_t(4 * NT) * kOutBytes + 256;
+  // TMEM columns: S_i fp32 [BK], O_i fp32 [64], P_i bf16 pairs [BK / 2]
+  static constexpr uint32_t kColS = 0, kColO = NT * BK, kColP = NT * BK + NT * FA_HD;
+  static constexpr int kSoftmaxRegs = NT == 2 ? 232 : 152;   // NT x 128 x regs + 128 x 40 <= 65 536
+  static_assert(kColP + NT * BK / 2 <= 512, "TMEM");
+  static_assert(kSmem <= 232448, "shared memory");
+  static_assert((NT * 128 * kSoftmaxRegs + 128 * 40) <= 65536, "registers");
+};
 // VAR bits (template parameter; A/B knobs, see launch_attention_tcgen05): 4 = in-kernel timeline trace,
 // 64 = split phases: a row's MUFU pairs first, under the tile's ping-pong turn (one warp saturates the XU pipe), the
 // turn is handed over, then the polynomial pairs (FMA pipe) run under the other tile's MUFU phase; without it POLY of
@@ -45,21 +64,12 @@ constexpr int FA_THREADS = 384;          // 12 warps: three full warpgroups (set
 constexpr int FA_VAR_INTERLEAVED = 0;
 constexpr int FA_VAR_SPLIT = 64;
 constexpr int FA_VAR_SPEC = 64 | 128;
-constexpr uint32_t FA_TILE_BYTES = FA_BQ * FA_HD * 2;      // 16 KB: one Q, K or V tile
-// Q is double buffered (2 x 2 tiles) so the next work item's queries load under the current item's last blocks
-// + 8 x 4 KB output staging (one 32-row x 128-byte tile per softmax warp, TMA-stored): 230 656 B of the 232 448 available
-constexpr uint32_t FA_OUT_BYTES = 32 * FA_HD * 2;
-constexpr size_t FA_SMEM = 1024 + size_t(4 + 2 * FA_STAGES) * FA_TILE_BYTES + 8 * FA_OUT_BYTES + 256;
-
-// TMEM columns
-constexpr uint32_t FA_COL_S = 0;      // S0 [0,128)  S1 [128,256)
-constexpr uint32_t FA_COL_O = 256;    // O0 [256,320) O1 [320,384)
-constexpr uint32_t FA_COL_P = 384;    // P0 [384,448) P1 [448,512)   (bf16 pairs: 64 columns per 128 keys)
-
+constexpr int FA_VAR_FREE = 16;
 struct FaParams {
   long long* dbg;      // timeline trace (VAR bit 2 only)
   int q_len, kv_len;
   int heads, q_blocks, n_items;      // work item w = (b * heads + head) * q_blocks + qb
+  int fence[3];                      // all 1: opaque conditions that split the staged exp2 pass into basic blocks
 };
 
 // Work item w = (b * heads + head) * q_blocks + qb, walked with stride gridDim.x.  The stride is decomposed once; each
@@ -94,33 +104,40 @@ struct FaItemWalk {
 
 #define FA_TRACE(slot, idx)                                                      \
   do {                                                                           \
-    if ((VAR & 4) && p.dbg && blockIdx.x == 0 && lane == 0 && (idx) < 256)       \
+    if ((VAR & 4) && NT == 2 && p.dbg && blockIdx.x == 0 && lane == 0 && (idx) < 256) \
       p.dbg[(slot) * 256 + (idx)] = clock64();                                   \
   } while (0)
 
 // Persistent: one CTA per SM loops over work items (256 queries of one (utterance, head)); TMEM, barriers and the
 // K/V ring live across items, the next item's Q / K / V loads and first QK^T run under the current item's tail, so
 // the ~4 us of per-CTA set-up and drain measured on the non-persistent version is paid once per launch.
-template <int VAR, int POLY>
-__global__ void __launch_bounds__(FA_THREADS, 1)
+template <int VAR, int POLY, int NT, int BK>
+__global__ void __launch_bounds__((FaCfg<NT, BK>::kThreads), 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                          const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_o,
                          const FaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                                   // 2 buffers x 2 tiles
-  uint8_t* sKV = smem + 4 * FA_TILE_BYTES;              // FA_STAGES x {K, V}
-  uint8_t* sOut = sKV + size_t(2 * FA_STAGES) * FA_TILE_BYTES;        // 8 warps x 4 KB (1024-byte aligned)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + 8 * FA_OUT_BYTES);
+  using Cfg = FaCfg<NT, BK>;
+  constexpr int FA_STAGES = Cfg::kStages;
+  constexpr uint32_t FA_TILE_BYTES = Cfg::kQTile, FA_KV_BYTES = Cfg::kKvTile, FA_OUT_BYTES = Cfg::kOutBytes;
+  constexpr uint32_t FA_COL_S = Cfg::kColS, FA_COL_O = Cfg::kColO, FA_COL_P = Cfg::kColP;
+  constexpr int FA_BK = BK;
+  constexpr int kTmaWarp = 4 * NT, kMmaWarp0 = 4 * NT + 1;      // the last warpgroup: TMA, NT MMA issuers, (idle)
+  constexpr int NC = BK / 32;                                   // 32-score chunks of a row
+  uint8_t* sQ = smem;                                   // 2 buffers x NT tiles
+  uint8_t* sKV = smem + size_t(2 * NT) * FA_TILE_BYTES; // FA_STAGES x {K, V}
+  uint8_t* sOut = sKV + size_t(2 * FA_STAGES) * FA_KV_BYTES;          // 4 NT warps x 4 KB (1024-byte aligned)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + size_t(4 * NT) * FA_OUT_BYTES);
   uint64_t* q_full = bars;                              // [2]
   uint64_t* q_empty = bars + 2;                         // [2]  all QK^T of the item retired (MMA -> producer)
   uint64_t* kv_full = bars + 4;                         // [FA_STAGES]
   uint64_t* kv_empty = kv_full + FA_STAGES;             // [FA_STAGES]
-  uint64_t* s_full = kv_empty + FA_STAGES;              // [2]  S_i ready               (MMA -> softmax)
-  uint64_t* s_free = s_full + 2;                        // [2]  S_i read from TMEM      (softmax -> MMA), 4 warp arrivals
-  uint64_t* p_full = s_free + 2;                        // [2]  P_i written             (softmax -> MMA), 4 warp arrivals
-  uint64_t* o_full = p_full + 2;                        // [2]  P_i V done              (MMA -> softmax)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* s_full = kv_empty + FA_STAGES;              // [NT]  S_i ready               (MMA -> softmax)
+  uint64_t* s_free = s_full + NT;                       // [NT]  S_i read from TMEM      (softmax -> MMA), 4 warp arrivals
+  uint64_t* p_full = s_free + NT;                       // [NT]  P_i written             (softmax -> MMA), 4 warp arrivals
+  uint64_t* o_full = p_full + NT;                       // [NT]  P_i V done              (MMA -> softmax)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + NT);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -135,13 +152,13 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
     tma_prefetch_desc(&tma_o);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&q_full[s], 1);
-      mbar_init(&q_empty[s], 2);            // one tcgen05.commit per MMA issuer
+      mbar_init(&q_empty[s], NT);           // one tcgen05.commit per MMA issuer
     }
     for (int s = 0; s < FA_STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 2);
+      mbar_init(&kv_empty[s], NT);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NT; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&s_free[i], 4);
       mbar_init(&p_full[i], 4);
@@ -149,7 +166,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
     }
     fence_barrier_init();
   }
-  if (warp == 9) {
+  if (warp == kMmaWarp0) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -160,15 +177,15 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
 
   // Producer and MMA warps run warp-uniform loops and elect one lane around the TMA / tcgen05 instructions (inside an
   // `if (lane == 0)` region every UTCHMMA is wrapped in an ELECT loop: ~90 cycles per MMA, measured with FA_TRACE).
-  // Register reallocation between warpgroups (setmaxnreg): the softmax threads hold a whole 128-score row and
-  // schedule their exp2 phase far better with 232 registers; the TMA / MMA warps need almost nothing.
+  // Register reallocation between warpgroups (setmaxnreg): the softmax threads hold a whole score row and schedule
+  // their exp2 phase far better with 232 registers (2 x 128; 152 for 3 x 64); the TMA / MMA warps need almost nothing.
   // 256 x 232 + 128 x 40 <= 384 x 168.  (The instruction sits at the head of each role's branch: ptxas budgets
   // registers per region it dominates.)
 #define FA_REGS_SMALL() asm volatile("setmaxnreg.dec.sync.aligned.u32 40;")
-#define FA_REGS_LARGE() asm volatile("setmaxnreg.inc.sync.aligned.u32 232;")
-  if (warp == 11) {
-    FA_REGS_SMALL();        // idle: only completes the third warpgroup
-  } else if (warp == 8) {
+#define FA_REGS_LARGE() asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::kSoftmaxRegs))
+  if (warp > kMmaWarp0 + NT - 1) {
+    FA_REGS_SMALL();        // idle: only completes the last warpgroup
+  } else if (warp == kTmaWarp) {
     // ===================== TMA producer =====================
     FA_REGS_SMALL();
     int stage = 0;
@@ -177,23 +194,24 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
     for (int it = 0; it < my_items; ++it, walk.next(p.q_blocks, p.heads)) {
       const int head = walk.head;
       const int b = walk.b;
-      const int q0 = walk.qb * (2 * FA_BQ);
+      const int q0 = walk.qb * (NT * FA_BQ);
       const int qbuf = it & 1;
       mbar_wait_relaxed(&q_empty[qbuf], uint32_t(((it >> 1) & 1) ^ 1));
       if (elect_one()) {
-        uint8_t* sq = sQ + size_t(2 * qbuf) * FA_TILE_BYTES;
-        mbar_expect_tx(&q_full[qbuf], 2 * FA_TILE_BYTES);
-        tma_load_3d(sq, &tma_q, &q_full[qbuf], head * FA_HD, q0, b);
-        tma_load_3d(sq + FA_TILE_BYTES, &tma_q, &q_full[qbuf], head * FA_HD, q0 + FA_BQ, b);
+        uint8_t* sq = sQ + size_t(NT * qbuf) * FA_TILE_BYTES;
+        mbar_expect_tx(&q_full[qbuf], NT * FA_TILE_BYTES);
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+          tma_load_3d(sq + size_t(t) * FA_TILE_BYTES, &tma_q, &q_full[qbuf], head * FA_HD, q0 + t * FA_BQ, b);
       }
       __syncwarp();
       for (int j = 0; j < n_blocks; ++j) {
         mbar_wait_relaxed(&kv_empty[stage], phase ^ 1);
-        uint8_t* sk = sKV + size_t(2 * stage) * FA_TILE_BYTES;
+        uint8_t* sk = sKV + size_t(2 * stage) * FA_KV_BYTES;
         if (elect_one()) {
-          mbar_expect_tx(&kv_full[stage], 2 * FA_TILE_BYTES);
+          mbar_expect_tx(&kv_full[stage], 2 * FA_KV_BYTES);
           tma_load_3d(sk, &tma_k, &kv_full[stage], head * FA_HD, j * FA_BK, b);
-          tma_load_3d(sk + FA_TILE_BYTES, &tma_v, &kv_full[stage], head * FA_HD, j * FA_BK, b);
+          tma_load_3d(sk + FA_KV_BYTES, &tma_v, &kv_full[stage], head * FA_HD, j * FA_BK, b);
         }
         __syncwarp();
         if (++stage == FA_STAGES) {
@@ -202,21 +220,22 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
         }
       }
     }
-  } else if (warp == 9 || warp == 10) {
-    // ===================== MMA issuers: warp 9 drives query tile 0, warp 10 tile 1 =====================
+  } else if (warp >= kMmaWarp0) {
+    // ===================== MMA issuers: one warp per query tile =====================
     // One issuing thread per tile, so neither tile's GEMMs ever queue behind a barrier that only the other tile's
     // softmax warps can satisfy (with a single issuer and a fixed wait order the two warpgroups throttled each other).
     FA_REGS_SMALL();
-    const int i = warp - 9;
+    const int i = warp - kMmaWarp0;
     constexpr uint32_t idesc_qk = umma_idesc(FA_BQ, FA_BK, 1, 0, 0);        // A, B K-major
     constexpr uint32_t idesc_pv = umma_idesc(FA_BQ, FA_HD, 1, 0, 1);        // A from TMEM, B (V) MN-major
     // No integer division in this loop: I2F / MUFU.RCP / F2I queue behind the softmax warps' exponentials on the XU
     // pipe (in-kernel timeline: 600-700 cycles per loop step, which left the issuers with no slack at all), so the
     // position of the block whose QK^T is issued next (one ahead of the block whose P V is issued) is carried along.
-    constexpr uint64_t kPairStep = (2 * FA_TILE_BYTES) >> 4;     // descriptor address units between Q buffers / stages
+    constexpr uint64_t kQBufStep = (NT * FA_TILE_BYTES) >> 4;    // descriptor address units between the Q buffers
+    constexpr uint64_t kStageStep = (2 * FA_KV_BYTES) >> 4;      // ... and between K/V ring stages
     const uint64_t da_base = umma_desc_k_sw128(smem_u32(sQ + size_t(i) * FA_TILE_BYTES));
     const uint64_t db_base = umma_desc_k_sw128(smem_u32(sKV));
-    const uint64_t dv_base = umma_desc_mn_sw128(smem_u32(sKV + FA_TILE_BYTES), 0);
+    const uint64_t dv_base = umma_desc_mn_sw128(smem_u32(sKV + FA_KV_BYTES), 0);
     int nj = 0, nit = 0, nstage = 0;            // next QK^T: key block within its item, item, K/V ring stage
     uint32_t nphase = 0;
     // everything that block needs from the producer: its K/V stage and, on the first block of an item, the item's Q
@@ -230,8 +249,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
       tc_fence_after();
     };
     auto issue_qk_next = [&]() {
-      const uint64_t da = da_base + uint64_t(nit & 1) * kPairStep;
-      const uint64_t db = db_base + uint64_t(nstage) * kPairStep;
+      const uint64_t da = da_base + uint64_t(nit & 1) * kQBufStep;
+      const uint64_t db = db_base + uint64_t(nstage) * kStageStep;
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < FA_HD / 16; ++k)
@@ -251,9 +270,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
     };
     if (total_g > 0) {
       wait_inputs_next(nullptr, 0);
-      // tile 1 starts half a block behind tile 0 (when tile 0's first S tile has been read), so that one warpgroup
-      // is in its exp2-heavy pass while the other reads / reduces scores instead of both hitting the MUFU together
-      if (i == 1) mbar_wait(&s_free[0], 0);
+      // tile i starts when tile i - 1 has read its first S tile, so that one warpgroup is in its exp2-heavy pass
+      // while the next reads / reduces scores instead of all hitting the MUFU together
+      if (i > 0) mbar_wait(&s_free[i - 1], 0);
       issue_qk_next();
     }
     int j = 0, stage = 0, qbuf = 0;             // the block whose P V is issued
@@ -268,11 +287,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
       mbar_wait(&p_full[i], uint32_t(g & 1));
       FA_TRACE(2 + i, g * 8 + 2);
       tc_fence_after();
-      const uint64_t dv = dv_base + uint64_t(stage) * kPairStep;
+      const uint64_t dv = dv_base + uint64_t(stage) * kStageStep;
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < FA_BK / 16; ++k)     // 16 keys per MMA: 8 TMEM columns of P, 2048 B of V
-          umma_ts(tmem_base + FA_COL_O + uint32_t(i * FA_HD), tmem_base + FA_COL_P + uint32_t(i * 64 + k * 8),
+          umma_ts(tmem_base + FA_COL_O + uint32_t(i * FA_HD), tmem_base + FA_COL_P + uint32_t(i * (BK / 2) + k * 8),
                   dv + uint64_t(k * (2048 >> 4)), idesc_pv, (j | k) != 0 ? 1u : 0u);
         umma_commit(&o_full[i]);
         umma_commit(&kv_empty[stage]);                                   // needs both tiles' commits
@@ -287,19 +306,32 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
       if (++stage == FA_STAGES) stage = 0;
     }
   } else {
-    // ===================== softmax + output (warps 0-7) =====================
+    // ===================== softmax + output (warps 0 .. 4 NT - 1) =====================
     FA_REGS_LARGE();
     const int i = warp >> 2;                        // query tile
     const int q = warp & 3;                         // TMEM lane quarter
     const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16);
     const uint32_t t_s = lane_base + FA_COL_S + uint32_t(i * FA_BK);
     const uint32_t t_o = lane_base + FA_COL_O + uint32_t(i * FA_HD);
-    const uint32_t t_p = lane_base + FA_COL_P + uint32_t(i * 64);
+    const uint32_t t_p = lane_base + FA_COL_P + uint32_t(i * (BK / 2));
     const float kLog2e = 1.4426950408889634f;
     constexpr bool kSplit = (VAR & 64) != 0;
     constexpr bool kSpec = (VAR & 128) != 0;
-    constexpr int kMuPairs = 64 - 4 * POLY;         // split phases: pairs [0, kMuPairs) of a row on the MUFU
-    if (i == 1 && total_g > 0) asm volatile("bar.arrive 1, 256;" ::: "memory");      // tile 0 takes the first turn
+    constexpr int kMuPairs = NC * (16 - POLY);      // split phases: pairs [0, kMuPairs) of a row on the MUFU
+    // Ping-pong turn (named barrier 1 + i belongs to tile i; 128 arriving + 128 waiting threads): the tiles take the
+    // exp2-heavy part of their blocks in rotation 0, 1, .., NT - 1, 0, ..
+    // (VAR bit 4: no turns, the tiles run free)
+    constexpr bool kTurns = (VAR & 16) == 0;
+    auto turn_wait = [&]() {
+      if constexpr (kTurns) asm volatile("bar.sync %0, 256;" ::"r"(1 + i) : "memory");
+    };
+    auto turn_pass = [&](int g_now) {
+      if constexpr (kTurns) {
+        if (i + 1 < NT) asm volatile("bar.arrive %0, 256;" ::"r"(2 + i) : "memory");
+        else if (g_now + 1 < total_g) asm volatile("bar.arrive 1, 256;" ::: "memory");
+      }
+    };
+    if (kTurns && i == NT - 1 && total_g > 0) asm volatile("bar.arrive 1, 256;" ::: "memory");      // tile 0 takes the first turn
     int g = 0;
     bool s_ready = false;            // early poll of s_full for the block about to start
     // ---- output of a finished item: O_i / l (called once the item's last P V may be waited for; g = blocks done) ----
@@ -349,7 +381,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
     for (int it = 0; it < my_items; ++it, walk.next(p.q_blocks, p.heads)) {
       const int head = walk.head;
       const int b = walk.b;
-      const int row = walk.qb * (2 * FA_BQ) + i * FA_BQ + q * 32 + lane;   // query index within the utterance
+      const int row = walk.qb * (NT * FA_BQ) + i * FA_BQ + q * 32 + lane;   // query index within the utterance
       float m_used = -INFINITY;      // stale running maximum (raw score units)
       float l_run = 0.f;
       bool pending = false;          // P of the previous block written but not yet signalled
@@ -368,9 +400,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
         // warps with two threads per row; refilling each chunk's registers with the next block's scores under the
         // exponentials.)
         const int valid = p.kv_len - j * FA_BK;       // keys of this block that exist
-        uint32_t r[4][32];
-        tmem_ld_32x32b_x32(t_s, r[0]);
-        tmem_ld_32x32b_x32(t_s + 32, r[1]);
+        uint32_t r[NC][32];
+#pragma unroll
+        for (int c = 0; c < NC / 2; ++c) tmem_ld_32x32b_x32(t_s + uint32_t(c * 32), r[c]);
         if (pending) {
           // P of the previous block: its stores are waited for only now, under the latency of the loads above
           tmem_st_wait();
@@ -379,8 +411,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
           if (lane == 0) mbar_arrive(&p_full[i]);
           pending = false;
         }
-        tmem_ld_32x32b_x32(t_s + 64, r[2]);
-        tmem_ld_32x32b_x32(t_s + 96, r[3]);
+#pragma unroll
+        for (int c = NC / 2; c < NC; ++c) tmem_ld_32x32b_x32(t_s + uint32_t(c * 32), r[c]);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
@@ -388,7 +420,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
         FA_TRACE(i, g * 8 + 3);
         if (valid < FA_BK) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
+          for (int c = 0; c < NC; ++c)
             if (valid < (c + 1) * 32) {               // warp-uniform: only the chunks that reach past the last key
 #pragma unroll
               for (int e = 0; e < 32; ++e)
@@ -402,10 +434,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
 #pragma unroll
           for (int c = 0; c < kChains; ++c) mxc[c] = -INFINITY;
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
+          for (int c = 0; c < NC; ++c)
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
-              const int ch = (kChains == 8) ? 2 * c + e / 16 : c;
+              constexpr int kPer = kChains / NC;      // chains per chunk
+              const int ch = c * kPer + e / (32 / kPer);
               mxc[ch] = fmaxf(mxc[ch], __uint_as_float(r[c][e]));
             }
           float mx = fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3]));
@@ -460,16 +493,13 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
           const float c0 = (126.0f + neg_m) * (1.0f / 252.0f);
           uint64_t sum2 = f2_pack(0.f, 0.f);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < NC; ++c) {
             uint32_t pk[16];
-            if (kTurn && c == 3) s_ready = (g + 1 < total_g) && mbar_try_wait(&s_full[i], uint32_t((g + 1) & 1));
+            if (kTurn && c == NC - 1) s_ready = (g + 1 < total_g) && mbar_try_wait(&s_full[i], uint32_t((g + 1) & 1));
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
               if constexpr (kTurn && kSplit && POLY > 0) {
-                if (c * 16 + e == kMuPairs) {                   // MUFU phase over: the other tile's turn
-                  if (i == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");
-                  else if (g + 1 < total_g) asm volatile("bar.arrive 1, 256;" ::: "memory");
-                }
+                if (c * 16 + e == kMuPairs) turn_pass(g);       // MUFU phase over: the next tile's turn
               }
               // split phases: the last 4 * POLY pairs of the row; otherwise POLY of every 16, evenly spread
               const bool use_poly = POLY > 0 && (kSplit ? (c * 16 + e >= kMuPairs) : (((e * POLY) & 15) < POLY));
@@ -500,12 +530,92 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
             }
             tmem_st_32x32b_x16(t_p + uint32_t(c * 16), pk);
             if constexpr (kTurn && !(kSplit && POLY > 0)) {
-              if (c == 2) {                                     // hand the turn over one chunk early
-                if (i == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");
-                else if (g + 1 < total_g) asm volatile("bar.arrive 1, 256;" ::: "memory");
-              }
+              if (c == NC - 2) turn_pass(g);                    // hand the turn over one chunk early
             }
           }
+          float sum0, sum1;
+          f2_unpack(sum2, sum0, sum1);
+          return sum0 + sum1;
+        };
+
+        // Staged pass (VAR bit 3; split phases, 2 x 128 only).  ptxas places each MUFU pair's consumers (FADD2, F2FP) right
+        // behind the NEXT pair's MUFUs, i.e. ~16 issue cycles after the producer, but MUFU.EX2 results take ~40: the
+        // in-order warp stalls on every pair and the MUFU phase runs at ~30 cycles per pair instead of 16 (in-kernel
+        // timeline; XU pipe 55 % busy under the turn).  Here a chunk's 32 exponentials are issued back to back, in
+        // place, and consumed one stage later, next to the following chunk's exponentials; the stages sit in separate
+        // basic blocks (opaque always-true conditions), which the scheduler does not mix.
+        auto exp_pass_staged = [&](bool rescale, float alpha) {
+          static_assert(NC == 4 || !(VAR & 8), "staged pass: 2 x 128 geometry");
+          constexpr int kMu2 = kMuPairs - 32;               // MUFU pairs of chunk 2
+          bool o_ready = false;
+          if (j > 0) o_ready = mbar_try_wait(&o_full[i], uint32_t((g - 1) & 1));
+          const float neg_m = -m_used * kLog2e;
+          const uint64_t negm2 = f2_pack(neg_m, neg_m);
+          const uint64_t log2e2 = f2_pack(kLog2e, kLog2e);
+          uint64_t sum2 = f2_pack(0.f, 0.f);
+          auto mufu_pairs = [&](int c, int n) {             // r[c][0 .. 2n) <- 2^(...) in place
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              if (e < n) {
+                float t0, t1;
+                f2_unpack(f2_fma(f2_pack(__uint_as_float(r[c][2 * e]), __uint_as_float(r[c][2 * e + 1])), log2e2, negm2), t0, t1);
+                r[c][2 * e] = __float_as_uint(fast_exp2(t0));
+                r[c][2 * e + 1] = __float_as_uint(fast_exp2(t1));
+              }
+            }
+          };
+          auto consume_pairs = [&](int c, int n, uint32_t* pk) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              if (e < n) {
+                const float p0 = __uint_as_float(r[c][2 * e]), p1 = __uint_as_float(r[c][2 * e + 1]);
+                sum2 = f2_add(sum2, f2_pack(p0, p1));
+                pk[e] = pack_bf16x2(p0, p1);
+              }
+            }
+          };
+          uint32_t pk0[16], pk1[16], pk2[16], pk3[16];
+          if (p.fence[0]) mufu_pairs(0, 16);
+          if (p.fence[1]) {
+            mufu_pairs(1, 16);
+            consume_pairs(0, 16, pk0);
+          }
+          if (j > 0) {
+            // Only now is the previous block's P V needed: P_i has been consumed (it may be overwritten) and O_i is
+            // stable (it may be rescaled).
+            FA_TRACE(i, g * 8 + 4);
+            if (!o_ready) mbar_wait(&o_full[i], uint32_t((g - 1) & 1));
+            FA_TRACE(i, g * 8 + 5);
+            tc_fence_after();
+            if (rescale) rescale_o(alpha);
+          }
+          tmem_st_32x32b_x16(t_p, pk0);
+          if (p.fence[2]) {
+            mufu_pairs(2, kMu2);
+            consume_pairs(1, 16, pk1);
+          }
+          tmem_st_32x32b_x16(t_p + 16, pk1);
+          turn_pass(g);                                     // MUFU phase over: the next tile's turn
+          consume_pairs(2, kMu2, pk2);
+#pragma unroll
+          for (int e = kMu2; e < 16; ++e) {
+            const uint64_t t2 = f2_fma(f2_pack(__uint_as_float(r[2][2 * e]), __uint_as_float(r[2][2 * e + 1])), log2e2, negm2);
+            float p0, p1;
+            exp2_poly2(t2, p0, p1);
+            sum2 = f2_add(sum2, f2_pack(p0, p1));
+            pk2[e] = pack_bf16x2(p0, p1);
+          }
+          tmem_st_32x32b_x16(t_p + 32, pk2);
+          s_ready = (g + 1 < total_g) && mbar_try_wait(&s_full[i], uint32_t((g + 1) & 1));
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const uint64_t t2 = f2_fma(f2_pack(__uint_as_float(r[3][2 * e]), __uint_as_float(r[3][2 * e + 1])), log2e2, negm2);
+            float p0, p1;
+            exp2_poly2(t2, p0, p1);
+            sum2 = f2_add(sum2, f2_pack(p0, p1));
+            pk3[e] = pack_bf16x2(p0, p1);
+          }
+          tmem_st_32x32b_x16(t_p + 48, pk3);
           float sum0, sum1;
           f2_unpack(sum2, sum0, sum1);
           return sum0 + sum1;
@@ -528,9 +638,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
         // Ping-pong: the two tiles' exp2 phases alternate (named barriers 1 / 2, FA3-style) instead of drifting into
         // lock-step, where both warps of a scheduler fight for the MUFU queue and neither feeds the FMA pipe; the other
         // tile's TMEM loads, row maximum and waits run under this tile's exponentials.
-        if (i == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
-        else asm volatile("bar.sync 2, 256;" ::: "memory");
-        float bsum = exp_pass(std::true_type{}, any_grow, alpha);
+        turn_wait();
+        float bsum;
+        if constexpr ((VAR & 8) != 0) bsum = exp_pass_staged(any_grow, alpha);
+        else bsum = exp_pass(std::true_type{}, any_grow, alpha);
         if constexpr (kSpec) {
           if (!exact) {
             const bool bad = !(bsum < 1.0e30f);            // also catches inf and NaN
@@ -567,7 +678,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, 512);
+  if (warp == kMmaWarp0) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -592,7 +703,7 @@ extern "C" void taste_dbg_attention_trace(void* dev_buf) { g_fa_trace = static_c
 
 bool attention_tcgen05_eligible(const AttnDesc& d) {
   if (d.cu_q || d.cu_kv || d.causal) return false;
-  if (d.q_len < 2 * FA_BQ || d.kv_len < FA_BK) return false;           // small problems: the mma.sync kernel
+  if (d.q_len < 2 * FA_BQ || d.kv_len < 128) return false;             // small problems: the mma.sync kernel
   if ((reinterpret_cast<uintptr_t>(d.q) | reinterpret_cast<uintptr_t>(d.k) | reinterpret_cast<uintptr_t>(d.v) |
        reinterpret_cast<uintptr_t>(d.o)) & 15)
     return false;
@@ -603,31 +714,52 @@ bool attention_tcgen05_eligible(const AttnDesc& d) {
 int launch_attention_tcgen05(const AttnDesc& d, cudaStream_t stream) {
   EncodeTiledFn enc = get_tensor_map_encoder();
   if (!enc) return set_error(TASTE_E_NO_DEVICE, "cuTensorMapEncodeTiled entry point unavailable");
-  CUtensorMap mq, mk, mv, mo;
-  int rc;
-  if ((rc = make_map(enc, &mq, d.q, d.heads, d.q_len, d.batch, d.ldq))) return rc;
-  if ((rc = make_map(enc, &mk, d.k, d.heads, d.kv_len, d.batch, d.ldk))) return rc;
-  if ((rc = make_map(enc, &mv, d.v, d.heads, d.kv_len, d.batch, d.ldv))) return rc;
-  if ((rc = make_map(enc, &mo, d.o, d.heads, d.q_len, d.batch, d.ldo, 32))) return rc;      // one warp's rows per store
-  // compiled variants (VAR, POLY); FA_VAR_SPLIT with 5 polynomial pairs of 16 is the default, the others are A/B knobs (TASTE_FA_VAR / TASTE_FA_POLY)
+  // Compiled variants (VAR, POLY, NT, BK).  Default: split exp2 phases, 5 polynomial pairs of 16, 2 tiles x 128 keys.
+  // The others are A/B knobs: TASTE_FA_VAR, TASTE_FA_POLY, TASTE_FA_TILES ("3x64").
 #define FA_VARIANTS(X)                                                                                          \
-  X(FA_VAR_SPLIT, 5) X(FA_VAR_SPLIT, 6) X(FA_VAR_SPLIT | 4, 5) X(FA_VAR_SPLIT | 256, 5)                        \
-  X(FA_VAR_INTERLEAVED, 6) X(FA_VAR_INTERLEAVED, 0) X(FA_VAR_SPEC, 5) X(FA_VAR_SPEC | 4, 5)
+  X(FA_VAR_FREE, 4, 3, 64) X(FA_VAR_FREE, 6, 3, 64) X(FA_VAR_FREE, 0, 3, 64) X(FA_VAR_SPLIT, 5, 3, 64)          \
+  X(FA_VAR_FREE | 128, 6, 3, 64) X(FA_VAR_SPLIT, 5, 2, 64)                                                      \
+  X(FA_VAR_SPLIT, 5, 2, 128) X(FA_VAR_SPLIT, 6, 2, 128) X(FA_VAR_SPLIT | 4, 5, 2, 128)                          \
+  X(FA_VAR_SPLIT | 256, 5, 2, 128) X(FA_VAR_INTERLEAVED, 6, 2, 128) X(FA_VAR_INTERLEAVED, 0, 2, 128)            \
+  X(FA_VAR_SPEC, 5, 2, 128) X(FA_VAR_SPEC | 4, 5, 2, 128) X(FA_VAR_SPLIT | 8, 5, 2, 128)                        \
+  X(FA_VAR_SPLIT | 16, 5, 2, 128) X(FA_VAR_INTERLEAVED | 16, 6, 2, 128)
   static bool configured = false;
   if (!configured) {
-#define FA_CFG(V, P) TASTE_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<(V), (P)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM));
+#define FA_CFG(V, P, T, K)                                                                                         \
+  TASTE_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<(V), (P), T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)FaCfg<T, K>::kSmem));
     FA_VARIANTS(FA_CFG)
 #undef FA_CFG
     configured = true;
   }
   const char* ev = getenv("TASTE_FA_VAR");
-  const int var = ev ? atoi(ev) : -1;
+  const char* ep = getenv("TASTE_FA_POLY");          // "0" = every exponential on the MUFU
+  const char* et = getenv("TASTE_FA_TILES");
+  // default: 3 tiles x 64 keys, free-running, 4 of 16 pairs on the FMA pipe (0.95 ms per encoder layer against 1.00 ms
+  // for the best 2 x 128 variant: split phases under the ping-pong turn, 5 of 16).  With any knob set, the others
+  // default to the 2 x 128 family.
+  const bool knobs = ev || ep || et;
+  int want_var = ev ? atoi(ev) : (knobs ? FA_VAR_SPLIT : FA_VAR_FREE);
+  int want_poly = ep ? atoi(ep) : (knobs ? ((want_var & 64) ? 5 : 6) : 4);
+  int want_nt = knobs ? 2 : 3, want_bk = knobs ? 128 : 64;
+  if (et && sscanf(et, "%dx%d", &want_nt, &want_bk) != 2) return set_error(TASTE_E_ARG, "TASTE_FA_TILES: expected <tiles>x<keys>");
+  if (d.q_len < want_nt * FA_BQ) {                                     // short sequences: two tiles
+    if (!knobs) want_var = FA_VAR_SPLIT, want_poly = 5;
+    want_nt = 2, want_bk = 128;
+  }
+  CUtensorMap mq, mk, mv, mo;
+  int rc;
+  if ((rc = make_map(enc, &mq, d.q, d.heads, d.q_len, d.batch, d.ldq))) return rc;
+  if ((rc = make_map(enc, &mk, d.k, d.heads, d.kv_len, d.batch, d.ldk, want_bk))) return rc;
+  if ((rc = make_map(enc, &mv, d.v, d.heads, d.kv_len, d.batch, d.ldv, want_bk))) return rc;
+  if ((rc = make_map(enc, &mo, d.o, d.heads, d.q_len, d.batch, d.ldo, 32))) return rc;      // one warp's rows per store
   FaParams p;
   p.dbg = g_fa_trace;
   p.q_len = d.q_len;
   p.kv_len = d.kv_len;
   p.heads = d.heads;
-  p.q_blocks = (d.q_len + 2 * FA_BQ - 1) / (2 * FA_BQ);
+  p.fence[0] = p.fence[1] = p.fence[2] = 1;
+  p.q_blocks = (d.q_len + want_nt * FA_BQ - 1) / (want_nt * FA_BQ);
   p.n_items = p.q_blocks * d.heads * d.batch;
   static int n_sm = 0;
   if (n_sm == 0) {
@@ -640,19 +772,17 @@ int launch_attention_tcgen05(const AttnDesc& d, cudaStream_t stream) {
   const double pairs = double(d.batch) * d.q_len * d.kv_len;
   ProfScope ps(stream, d.kclass == KC_ATTN_ENC ? KC_ATTN_ENC : KC_ATTN_TC, 4.0 * pairs * FA_HD * d.heads,
                2.0 * FA_HD * d.heads * double(d.batch) * (2.0 * d.q_len + 2.0 * d.kv_len));
-  const char* ep = getenv("TASTE_FA_POLY");          // A/B knob: "0" = every exponential on the MUFU
-  const int want_var = var >= 0 ? var : FA_VAR_SPLIT;
-  const int want_poly = ep ? atoi(ep) : ((want_var & 64) ? 5 : 6);
   bool launched = false;
-#define FA_GO(V, P)                                                                                                   \
-  if (!launched && want_var == (V) && want_poly == (P)) {                                                             \
-    attention_tcgen05_kernel<(V), (P)><<<grid, FA_THREADS, FA_SMEM, stream>>>(mq, mk, mv, mo, p);                         \
-    launched = true;                                                                                                  \
+#define FA_GO(V, P, T, K)                                                                                           \
+  if (!launched && want_var == (V) && want_poly == (P) && want_nt == T && want_bk == K) {                            \
+    attention_tcgen05_kernel<(V), (P), T, K><<<grid, FaCfg<T, K>::kThreads, FaCfg<T, K>::kSmem, stream>>>(mq, mk, mv, mo, p); \
+    launched = true;                                                                                                \
   }
   FA_VARIANTS(FA_GO)
 #undef FA_GO
 #undef FA_VARIANTS
-  if (!launched) return set_error(TASTE_E_ARG, "attention: variant %d / poly %d is not compiled", want_var, want_poly);
+  if (!launched)
+    return set_error(TASTE_E_ARG, "attention: variant %d / poly %d / %dx%d is not compiled", want_var, want_poly, want_nt, want_bk);
   TASTE_CUDA_OK(cudaGetLastError());
   return 0;
 }

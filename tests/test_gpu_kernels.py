@@ -198,7 +198,8 @@ def test_attention_fixed(lib, B, S, H, mode):
     assert _rel(o.float(), ref) < 6e-3          # bf16 P and bf16 output rounding
 
 
-@pytest.mark.parametrize("variant", [None, (64, 6), (320, 5), (192, 5), (0, 6), (0, 0)])
+@pytest.mark.parametrize("variant", [None, (16, 6, "3x64"), (144, 6, "3x64"), (64, 5, "3x64"), (64, 5, "2x64"), (64, 5), (64, 6),
+                                     (320, 5), (192, 5), (72, 5), (80, 5), (0, 6), (0, 0)])
 @pytest.mark.parametrize("jump", [0.0, 30.0, 250.0])
 def test_attention_score_range(lib, variant, jump, monkeypatch):
     """Encoder kernel variants (TASTE_FA_VAR / TASTE_FA_POLY) on rows whose scores GROW along the key axis: later key
@@ -208,7 +209,12 @@ def test_attention_score_range(lib, variant, jump, monkeypatch):
     if variant is not None:
         monkeypatch.setenv("TASTE_FA_VAR", str(variant[0]))
         monkeypatch.setenv("TASTE_FA_POLY", str(variant[1]))
+        if len(variant) > 2:
+            monkeypatch.setenv("TASTE_FA_TILES", variant[2])
+        else:
+            monkeypatch.delenv("TASTE_FA_TILES", raising=False)
     else:
+        monkeypatch.delenv("TASTE_FA_TILES", raising=False)
         monkeypatch.delenv("TASTE_FA_VAR", raising=False)
         monkeypatch.delenv("TASTE_FA_POLY", raising=False)
     torch.manual_seed(11)
