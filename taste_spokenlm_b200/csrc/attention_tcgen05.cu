@@ -2,26 +2,32 @@
 // scores and accumulators.  Serves the encoder self-attention (CW:377-394 eager semantics: softmax(q k^T) v with q
 // pre-scaled, NO mask — JES:198-203), which is 16 % of the path's FLOPs.
 //
-// Persistent: one CTA per SM walks over work items of 256 queries of one (utterance, head), as two 128-row tiles:
-//   S_i = Q_i K_j^T   tcgen05.mma  SS  (M 128, N 128 keys, K 64)      -> TMEM, 128 fp32 columns per tile
+// Persistent: one CTA per SM walks over work items of NT x 128 queries of one (utterance, head), as NT 128-row tiles,
+// over key blocks of BK keys (default NT = 3, BK = 64; 2 x 128 is the other compiled geometry):
+//   S_i = Q_i K_j^T   tcgen05.mma  SS  (M 128, N BK keys, K 64)       -> TMEM, BK fp32 columns per tile
 //   softmax           one thread per query row reads its whole S row ONCE with tcgen05.ld (no shuffles) and hands S
 //                     back at once, keeps the running max / sum in registers, exponentiates in packed FFMA2 pairs
-//                     (MUFU ex2 for 10 of 16 pairs, a degree-3 polynomial on the FMA pipe for the other 6) and
+//                     (MUFU ex2 for 12 of 16 pairs, a degree-3 polynomial on the FMA pipe for the other 4) and
 //                     writes P (bf16) back to TMEM with tcgen05.st
-//   O_i += P_i V_j    tcgen05.mma  TS  (A = P from TMEM, B = V tile, MN-major; M 128, N 64, K 128 keys)
+//   O_i += P_i V_j    tcgen05.mma  TS  (A = P from TMEM, B = V tile, MN-major; M 128, N 64, K BK keys)
+//   output            O_i / l staged per warp in shared memory (128-byte swizzle) and written with TMA stores
 // Each tile has its own MMA-issuing warp, so the next block's QK^T of a tile runs under that tile's exponentials and
-// under the other tile's GEMMs.  Q (double buffered) and K/V (4-stage mbarrier ring) arrive by TMA (128-byte swizzle)
+// under the other tiles' GEMMs.  Q (double buffered) and K/V (4-stage mbarrier ring) arrive by TMA (128-byte swizzle)
 // straight from the packed [rows, 3*D] QKV activation.  The accumulator is rescaled only when a row's maximum grows by
 // more than 2^8 (the stale maximum keeps exp2 arguments <= 8, exact in fp32 / bf16 range), so the O read-modify-write
 // in TMEM is rare after the first key block.
 //
-// Roles (384 threads, three warpgroups): warps 0-3 softmax tile 0, warps 4-7 softmax tile 1 (warp w owns TMEM lanes
-// 32*(w%4)..+31), warp 8 TMA producer, warp 9 MMA issuer of tile 0 + TMEM allocator, warp 10 MMA issuer of tile 1,
-// warp 11 idle (it completes the third warpgroup so that setmaxnreg can move registers: softmax threads 232, the
-// rest 40 - the softmax thread holds a 128-score row and schedules its exp2 phase far better with the extra 64).
-// The two tiles' exp2 phases are ping-ponged with named barriers: left alone they drift into lock-step (measured with
-// the in-kernel timeline), where both warps of a scheduler stall on the MUFU queue and the block period grows by a
-// third.
+// Roles (NT x 128 + 128 threads): warps 0 .. 4 NT - 1 softmax (warp w: tile w / 4, TMEM lanes 32 * (w % 4) .. + 31),
+// then one TMA producer warp and NT MMA issuers (the first also allocates TMEM); with NT = 2 a twelfth, idle warp
+// completes the last warpgroup so that setmaxnreg can move registers to the softmax threads.
+// Scheduling of the softmax warpgroups, all measured on B200:
+//   3 x 64, free-running: three softmax warps per scheduler cover each other's MUFU / TMEM / mbarrier latencies
+//                         (0.95 ms per encoder layer, batch 64);
+//   2 x 128, ping-pong  : with two warps per scheduler the tiles drift into lock-step when left alone, so their exp2
+//                         phases alternate under named barriers, MUFU pairs first, polynomial pairs after the
+//                         hand-over (1.00 ms).
+// Nothing in the per-block loops may touch the XU pipe except the exponentials: an integer division (I2F, MUFU.RCP,
+// F2I) in an MMA issuer queues behind them for hundreds of cycles.
 #include <stdio.h>
 #include <stdlib.h>
 
