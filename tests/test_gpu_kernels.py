@@ -170,7 +170,8 @@ def _attn_ref(q, k, v, causal):
 
 
 @pytest.mark.parametrize("B,S,H", [(1, 64, 1), (2, 1500, 3), (3, 200, 2), (2, 65, 2), (1, 256, 1), (2, 300, 2),
-                                   (1, 1536, 2), (3, 1000, 4), (1, 257, 1)])
+                                   (1, 1536, 2), (3, 1000, 4), (1, 257, 1),
+                                   (40, 400, 5), (9, 777, 6)])      # more work items than SMs: the persistent walk
 @pytest.mark.parametrize("mode", [0, 1])
 def test_attention_fixed(lib, B, S, H, mode):
     """mode 0: tcgen05/TMEM kernel when S >= 256 (encoder shape), mode 1: mma.sync kernel everywhere."""
