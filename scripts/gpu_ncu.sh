@@ -15,7 +15,7 @@ echo "ncu gemm exit $?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:attention_tcgen05 -s 100 -c 1 \
     -o gpurun_out/prof_attn_$TAG -f $CMD > gpurun_out/ncu_attn.log 2>&1
 echo "ncu attn exit $?"
-timeout 900 ncu --set full --clock-control none -k regex:'layernorm_kernel|logmel_tile|rvq_encode' -s 200 -c 3 \
+timeout 900 ncu --set full --clock-control none -k regex:'layernorm_kernel|logmel_tile|logmel_finish|rvq_encode|resample|word_pool' -s 130 -c 40 \
     -o gpurun_out/prof_misc_$TAG -f $CMD > gpurun_out/ncu_misc.log 2>&1
 echo "ncu misc exit $?"
 ls -la gpurun_out/*$TAG*.ncu-rep
