@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TASTE_ABI_VERSION 2
+#define TASTE_ABI_VERSION 3
 
 #define TASTE_E_ARG        (-1)  /* null pointer / bad size */
 #define TASTE_E_SHAPE      (-2)  /* geometry not supported by the kernels (see taste_handle_create) */
@@ -43,6 +43,8 @@ extern "C" {
 #define TASTE_N_MELS     128
 #define TASTE_ENC_FRAMES 1500
 #define TASTE_DFT_LD     224      /* padded leading dim of the DFT tables */
+#define TASTE_DFT_K      448      /* tensor-core DFT: samples per frame slab (400, zero-weighted up to 7 x 64) */
+#define TASTE_DFT_N      512      /* ... output columns: Re X[0..200] at 0, Im X[0..200] at 256, rest zero */
 
 typedef struct taste_handle_s* taste_handle_t;
 
@@ -101,6 +103,9 @@ typedef struct {
   const int32_t* mel_start;     /* [128] first non-zero bin of each mel filter */
   const int32_t* mel_count;     /* [128] number of non-zero bins */
   const float*   mel_weight;    /* [128][TASTE_MEL_MAXW] non-zero weights, zero padded */
+  /* tensor-core DFT (nullable: then the fp32 FMA kernel runs): bf16 [TASTE_DFT_N][3 * TASTE_DFT_K], row j = output
+   * column j, K slabs {hi(t), lo(t), hi(t)} of t[j][n] = hann[n] * cos|sin(2*pi*bin*n/400) (split bf16, see logmel.cu) */
+  const void*    dft_w_bf16;
   /* encoder stem (JES:174-181) */
   const void*  conv1_w;  const float* conv1_b;   /* bf16 [D, 3*128], k = tap*128 + c */
   const void*  conv2_w;  const float* conv2_b;   /* bf16 [D, 3*D],   k = tap*D + c */
@@ -227,6 +232,9 @@ int taste_gemm_ex(const taste_gemm_ex_t* g, void* stream);
  * weights are present and the batch has >= 2048 rows (final_layer_norm stays a kernel), 1 = always run the separate
  * LayerNorm kernels, 2 = fold both LayerNorms (measured slower; A/B only). */
 int taste_encoder_set_mode(int mode);
+/* Front-end formulation for A/B timing and tests: 0 = split-bf16 DFT on the tcgen05 GEMM kernel when dft_w_bf16 is
+ * present (default), 1 = the fp32 folded-DFT FMA kernel.  Process-wide. */
+int taste_logmel_set_mode(int mode);
 /* Tile-shape override for A/B timing and tests: 0 = automatic (CTA pairs, 256 x 256 tiles, when one wave of pair tiles
  * exists), 1 = always the single-CTA 128 x {256,128} kernel.  Process-wide. */
 int taste_gemm_set_mode(int mode);

@@ -47,7 +47,7 @@ class DecLayer(C.Structure):
 
 class Weights(C.Structure):
     _fields_ = [("dims", Dims)] + [(n, p) for n in (
-        "dft_cos", "dft_sin", "hann", "mel_start", "mel_count", "mel_weight",
+        "dft_cos", "dft_sin", "hann", "mel_start", "mel_count", "mel_weight", "dft_w_bf16",
         "conv1_w", "conv1_b", "conv2_w", "conv2_b", "enc_pos", "enc", "enc_ln_w", "enc_ln_b",
         "tok_emb", "dec_pos", "dec", "dec_ln_w", "dec_ln_b",
         "rvq_win_t", "rvq_bin", "rvq_code_t", "rvq_code", "rvq_code_sq", "rvq_wout_t", "rvq_bout")]
@@ -81,6 +81,7 @@ _SIGS = {
     "taste_gemm_bf16": (C.c_int, [p, p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, p]),
     "taste_gemm_ex": (C.c_int, [C.POINTER(GemmEx), p]),
     "taste_encoder_set_mode": (C.c_int, [C.c_int]),
+    "taste_logmel_set_mode": (C.c_int, [C.c_int]),
     "taste_attention_set_mode": (C.c_int, [C.c_int]),
     "taste_gemm_set_mode": (C.c_int, [C.c_int]),
     "taste_layernorm_f32": (C.c_int, [p, p, p, p, C.c_int, C.c_int, C.c_int, p]),

@@ -95,6 +95,8 @@ AggWs carve_aggregator(const taste_dims_t& d, int batch, int sum_tokens, void* w
 struct MelWs {
   float* logspec;
   unsigned int* umax;
+  void* planes;        // tensor-core DFT: split waveform
+  float* spectrum;     // ... and its fp32 spectrum
   size_t bytes;
 };
 MelWs carve_logmel(int batch, void* ws) {
@@ -102,6 +104,8 @@ MelWs carve_logmel(int batch, void* ws) {
   MelWs m;
   m.logspec = static_cast<float*>(c.take(size_t(batch) * TASTE_N_FRAMES * TASTE_N_MELS * 4));
   m.umax = static_cast<unsigned int*>(c.take(size_t(batch) * 4));
+  m.planes = c.take(size_t(batch) * 2 * size_t(LOGMEL_PLANE) * 2);
+  m.spectrum = static_cast<float*>(c.take(size_t(batch) * TASTE_N_FRAMES * TASTE_DFT_N * 4));
   m.bytes = c.off;
   return m;
 }
@@ -157,8 +161,8 @@ int taste_logmel_f32(taste_handle_t h, const float* wav, const int32_t* n_sample
   if (!ws) return set_error(TASTE_E_ARG, "logmel: null workspace");
   MelWs m = carve_logmel(batch, ws);
   if (m.bytes > ws_bytes) return set_error(TASTE_E_WORKSPACE, "logmel: workspace %zu < %zu", ws_bytes, m.bytes);
-  return launch_logmel(h->w, wav, n_samples, batch, wav_stride, feats_f32, feats_bf16, m.logspec, m.umax,
-                       static_cast<cudaStream_t>(stream));
+  return launch_logmel(h->w, wav, n_samples, batch, wav_stride, feats_f32, feats_bf16, m.logspec, m.umax, m.planes,
+                       m.spectrum, static_cast<cudaStream_t>(stream));
 }
 
 int taste_encoder_fwd(taste_handle_t h, const float* feats_f32, const void* feats_bf16, int batch, void* h_last_bf16,
@@ -421,6 +425,12 @@ int taste_gemm_bf16(const void* a, const void* w, const float* bias, void* out, 
                     void* stream) {
   if (epilogue < 0 || epilogue > 3) return set_error(TASTE_E_ARG, "gemm: epilogue must be 0..3");
   return gemm_plain(a, w, bias, out, m, n, k, epilogue, static_cast<cudaStream_t>(stream));
+}
+
+int taste_logmel_set_mode(int mode) {
+  if (mode < 0 || mode > 1) return set_error(TASTE_E_ARG, "logmel_set_mode: mode must be 0 or 1");
+  set_logmel_mode(mode);
+  return 0;
 }
 
 int taste_encoder_set_mode(int mode) {

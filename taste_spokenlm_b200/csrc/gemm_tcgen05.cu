@@ -44,6 +44,8 @@ struct GemmParams {
   const float* ln_colsum;     // [n]
   float* stats_out;           // [rows][n / 128][2]
   __nv_bfloat16* out_bf16;    // [rows, ldc]
+  int kclass;                 // host-side accounting only
+  double alg_bytes;
 };
 
 template <int BN>
@@ -667,7 +669,7 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
   const double m = double(p.rows_out) * (p.total_tiles / (p.n_tiles * p.m_tiles_per_batch));
   const double n = double(p.n_tiles) * BN, k = double(p.taps) * p.kb_per_tap * BK;
   const double out_b = (EPI == EPI_BF16 || EPI == EPI_GELU_BF16) ? 2.0 : (EPI == EPI_RESID_F32 ? 8.0 : 4.0);
-  ProfScope ps(stream, KC_GEMM, 2.0 * m * n * k, 2.0 * (m * k / p.taps + n * k) + out_b * m * n);
+  ProfScope ps(stream, p.kclass, 2.0 * m * n * k, p.alg_bytes >= 0 ? p.alg_bytes : 2.0 * (m * k / p.taps + n * k) + out_b * m * n);
   kern<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, stream>>>(ta, tb, p);
   TASTE_CUDA_OK(cudaGetLastError());
   return 0;
@@ -700,7 +702,7 @@ static int launch_cfg2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   const double m = double(p.rows_out) * (p.total_tiles / (p.n_tiles * p.m_tiles_per_batch));
   const double n = double(p.n_tiles) * BN2, k = double(p.taps) * p.kb_per_tap * BK;
   const double out_b = (EPI == EPI_BF16 || EPI == EPI_GELU_BF16) ? 2.0 : (EPI == EPI_RESID_F32 ? 8.0 : 4.0);
-  ProfScope ps(stream, KC_GEMM, 2.0 * m * n * k, 2.0 * (m * k / p.taps + n * k) + out_b * m * n);
+  ProfScope ps(stream, p.kclass, 2.0 * m * n * k, p.alg_bytes >= 0 ? p.alg_bytes : 2.0 * (m * k / p.taps + n * k) + out_b * m * n);
   kern<<<2 * pairs, kGemm2Threads, Gemm2Cfg::kSmemBytes, stream>>>(ta, tb, p);
   TASTE_CUDA_OK(cudaGetLastError());
   return 0;
@@ -808,6 +810,8 @@ int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
   p.ln_colsum = d.ln_colsum;
   p.stats_out = d.stats_out;
   p.out_bf16 = static_cast<__nv_bfloat16*>(d.out_bf16);
+  p.kclass = d.kclass;
+  p.alg_bytes = d.alg_bytes;
   if (use_pair) return launch_epi2(ta, tb, p, d.epilogue, ln, stream);
   return bn == 256 ? launch_epi<256>(ta, tb, p, d.epilogue, stream) : launch_epi<128>(ta, tb, p, d.epilogue, stream);
 }

@@ -20,7 +20,8 @@ int set_error(int code, const char* fmt, ...);
 // ---- launch accounting / device timing (prof.cu) ----
 enum KernelClass {
   KC_GEMM = 0, KC_ATTN_ENC, KC_ATTN_AGG, KC_LAYERNORM, KC_CAST, KC_LOGMEL_TILE, KC_LOGMEL_FINISH, KC_EMBED,
-  KC_WORD_POOL, KC_RVQ_ENCODE, KC_RVQ_DECODE, KC_MAP_LLM, KC_ATTN_TC, KC_RESAMPLE, KC_COUNT
+  KC_WORD_POOL, KC_RVQ_ENCODE, KC_RVQ_DECODE, KC_MAP_LLM, KC_ATTN_TC, KC_RESAMPLE, KC_LOGMEL_SPLIT, KC_LOGMEL_DFT,
+  KC_LOGMEL_MEL, KC_COUNT
 };
 // Wrap a kernel launch: counts it and, when profiling is on, brackets it with CUDA events on `stream`.
 // flops / bytes are the ALGORITHMIC work of the launch (DESIGN.md "Kernels").
@@ -74,6 +75,9 @@ struct GemmDesc {
   float* stats_out = nullptr;         // producer: [rows][n/128][2]; requires out_bf16
   void* out_bf16 = nullptr;
   bool force_pair = false;
+  // accounting (prof.cu): kernel class and, when >= 0, the algorithmic bytes booked on this launch
+  int kclass = KC_GEMM;
+  double alg_bytes = -1.0;
 };
 int launch_gemm(const GemmDesc& d, cudaStream_t stream);
 void set_gemm_mode(int mode);
@@ -111,9 +115,13 @@ int launch_map_llm(const int64_t* asr_indices, const int32_t* asr_wid, const int
                    const int32_t* llm_len, int batch, int tmax, int lmax, int nq, int64_t* out, cudaStream_t stream);
 
 // ---- log-mel (logmel.cu) ----
+// planes: bf16 [batch][2][LOGMEL_PLANE] (hi / lo halves of the reflect-padded waveform), spectrum: fp32
+// [batch * 3000][TASTE_DFT_N]; both only used by the tensor-core formulation (may be null for the FMA kernel)
+constexpr int64_t LOGMEL_PLANE = int64_t(TASTE_HOP) * TASTE_N_FRAMES + TASTE_DFT_K;      // 480 448 samples
 int launch_logmel(const taste_weights_t& w, const float* wav, const int32_t* n_samples, int batch, int64_t wav_stride,
                   float* feats_f32, void* feats_bf16, float* scratch_logspec, unsigned int* scratch_max,
-                  cudaStream_t stream);
+                  void* scratch_planes, float* scratch_spectrum, cudaStream_t stream);
+void set_logmel_mode(int mode);
 
 // ---- RVQ (rvq.cu) ----
 int launch_rvq_encode(const taste_weights_t& w, const float* z, const int32_t* lengths, int batch, int tmax, int in_dim,

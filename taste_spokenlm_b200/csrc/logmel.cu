@@ -1,10 +1,17 @@
-// Whisper log-mel front-end (WF:56-113), fused per 64-frame tile:
-//   pad/trim to 30 s + reflect padding (index arithmetic, no padded copy) -> periodic-Hann window ->
-//   400-point real DFT, folded over the n <-> 400-n symmetry so only 199 x 201 twiddle products are needed per
-//   frame -> |X|^2 -> sparse Slaney mel projection (394 non-zeros) -> log10(clamp 1e-10) -> per-utterance max.
-// A second small kernel applies the `max - 8` floor and the (x+4)/4 scaling and emits fp32 and/or bf16 features.
-// Arithmetic is fp32 (packed FFMA2) throughout: the 80 dB dynamic range kept by the `max - 8` floor rules out a single
-// bf16 tensor-core pass (SURVEY §7 hard part 6).
+// Whisper log-mel front-end (WF:56-113):
+//   pad/trim to 30 s + reflect padding -> periodic-Hann window -> 400-point real DFT -> |X|^2 -> sparse Slaney mel
+//   projection (394 non-zeros) -> log10(clamp 1e-10) -> per-utterance max; a last small kernel applies the `max - 8`
+//   floor and the (x+4)/4 scaling and emits fp32 and/or bf16 features.
+// Two formulations of the DFT (taste_logmel_set_mode; ncu: profiles/r1v12_ncu_misc_summary.json and r1v13):
+//  0 (default) DFT-as-GEMM on the tcgen05 GEMM kernel.  bf16 alone cannot carry the 80 dB dynamic range kept by the
+//    `max - 8` floor (SURVEY 7 hard part 6), so samples and twiddles are split into bf16 halves, x = hi + lo (|lo| <=
+//    2^-9 |x|), and  x t ~= hi(x) hi(t) + hi(x) lo(t) + lo(x) hi(t)  (relative error ~2^-17, fp32 accumulation) is
+//    ONE GEMM with three K slabs.  logmel_split_kernel writes the reflect-padded waveform once as two bf16 planes;
+//    the frames are never materialised: the A operand is a 4-D tensor map over the planes whose row stride is the hop
+//    (160 samples = 320 bytes), so TMA reads the overlapping 448-sample slabs (400 + zero-weighted tail) directly;
+//    the Hann window is folded into the twiddle matrix; logmel_mel_kernel turns the fp32 spectrum into log-mel.
+//  1 fp32 FMA kernel, fused per 64-frame tile: the DFT folded over the n <-> 400-n symmetry so only 199 x 201 twiddle
+//    products are needed per frame (packed FFMA2).  Exact fp32 arithmetic, but latency-bound on its twiddle loads.
 #include "common.cuh"
 #include "internal.h"
 
@@ -175,6 +182,92 @@ logmel_tile_kernel(const float* __restrict__ wav, const int32_t* __restrict__ n_
   }
 }
 
+// ---- tensor-core formulation: split planes -> (GEMM) -> mel ----
+// planes[b][0 | 1][i], i in [0, LOGMEL_PLANE): hi / lo bf16 halves of the padded waveform sample i (reflect padding of
+// 200, zeros past the utterance and past the 30 s window).  8 samples per thread, 16-byte stores.
+__global__ void __launch_bounds__(256)
+logmel_split_kernel(const float* __restrict__ wav, const int32_t* __restrict__ n_samples, int64_t wav_stride,
+                    __nv_bfloat16* __restrict__ planes) {
+  const int b = blockIdx.y;
+  const int64_t i0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (i0 >= LOGMEL_PLANE) return;
+  const float* w = wav + int64_t(b) * wav_stride;
+  int n_valid = n_samples ? n_samples[b] : TASTE_N_SAMPLES;
+  n_valid = max(0, min(n_valid, TASTE_N_SAMPLES));
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float x[2], h[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int i = int(i0) + 2 * e + t;
+      x[t] = i < TASTE_N_SAMPLES + TASTE_N_FFT ? padded_sample(w, n_valid, i) : 0.f;
+      h[t] = __bfloat162float(__float2bfloat16_rn(x[t]));
+    }
+    hi[e] = pack_bf16x2(h[0], h[1]);
+    lo[e] = pack_bf16x2(x[0] - h[0], x[1] - h[1]);
+  }
+  __nv_bfloat16* p0 = planes + int64_t(b) * 2 * LOGMEL_PLANE + i0;
+  *reinterpret_cast<uint4*>(p0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(p0 + LOGMEL_PLANE) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// spectrum [b * 3000 + f][TASTE_DFT_N] (Re at column k, Im at 256 + k) -> power -> mel -> log10 -> logspec, running max.
+constexpr int MM_FRAMES = 32;
+__global__ void __launch_bounds__(256)
+logmel_mel_kernel(const float* __restrict__ spectrum, const int32_t* __restrict__ mel_start,
+                  const int32_t* __restrict__ mel_count, const float* __restrict__ mel_weight,
+                  float* __restrict__ logspec, unsigned int* __restrict__ umax) {
+  __shared__ float sP[MM_FRAMES * LM_LDP];
+  __shared__ float s_red[8];
+  const int b = blockIdx.y;
+  const int f0 = blockIdx.x * MM_FRAMES;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  // 16-byte loads, 51 per half row (bins 0..203; 201..203 are zero columns of the GEMM), four rows in flight per thread
+  constexpr int kQuads = 51;
+#pragma unroll 4
+  for (int idx = tid; idx < MM_FRAMES * 64; idx += 256) {
+    const int f = idx >> 6;
+    const int k4 = idx & 63;
+    if (k4 < kQuads && f0 + f < TASTE_N_FRAMES) {
+      const float4* row = reinterpret_cast<const float4*>(spectrum + (int64_t(b) * TASTE_N_FRAMES + f0 + f) * TASTE_DFT_N);
+      const float4 re = __ldg(row + k4), im = __ldg(row + 64 + k4);
+      float* dst = sP + f * LM_LDP + 4 * k4;
+      dst[0] = re.x * re.x + im.x * im.x;
+      dst[1] = re.y * re.y + im.y * im.y;
+      dst[2] = re.z * re.z + im.z * im.z;
+      dst[3] = re.w * re.w + im.w * im.w;
+    }
+  }
+  __syncthreads();
+  float lmax = -INFINITY;
+  const int m = tid & 127;
+  const int ms = __ldg(mel_start + m);
+  const int mc = __ldg(mel_count + m);
+  float wgt[TASTE_MEL_MAXW];
+#pragma unroll
+  for (int j = 0; j < TASTE_MEL_MAXW; ++j) wgt[j] = __ldg(mel_weight + m * TASTE_MEL_MAXW + j);
+  for (int f = tid >> 7; f < MM_FRAMES; f += 2) {
+    if (f0 + f >= TASTE_N_FRAMES) break;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < TASTE_MEL_MAXW; ++j)
+      if (j < mc) acc = fmaf(wgt[j], sP[f * LM_LDP + ms + j], acc);
+    const float lg = log10f(fmaxf(acc, 1e-10f));
+    logspec[(int64_t(b) * TASTE_N_FRAMES + f0 + f) * TASTE_N_MELS + m] = lg;
+    lmax = fmaxf(lmax, lg);
+  }
+  lmax = warp_max(lmax);
+  if (lane == 0) s_red[tid >> 5] = lmax;
+  __syncthreads();
+  if (tid == 0) {
+    float v = s_red[0];
+    for (int i = 1; i < 8; ++i) v = fmaxf(v, s_red[i]);
+    if (v > -INFINITY) atomicMax(umax + b, float_to_ordered(v));
+  }
+}
+
 __global__ void __launch_bounds__(256)
 logmel_finish_kernel(const float* __restrict__ logspec, const unsigned int* __restrict__ umax, float* __restrict__ out_f32,
                      __nv_bfloat16* __restrict__ out_bf16) {
@@ -198,9 +291,12 @@ logmel_finish_kernel(const float* __restrict__ logspec, const unsigned int* __re
   }
 }
 
+static int g_logmel_mode = 0;
+void set_logmel_mode(int mode) { g_logmel_mode = mode; }
+
 int launch_logmel(const taste_weights_t& w, const float* wav, const int32_t* n_samples, int batch, int64_t wav_stride,
                   float* feats_f32, void* feats_bf16, float* scratch_logspec, unsigned int* scratch_max,
-                  cudaStream_t stream) {
+                  void* scratch_planes, float* scratch_spectrum, cudaStream_t stream) {
   if (!wav || (!feats_f32 && !feats_bf16)) return set_error(TASTE_E_ARG, "logmel: null pointer");
   if (!w.dft_cos || !w.dft_sin || !w.hann || !w.mel_start || !w.mel_count || !w.mel_weight)
     return set_error(TASTE_E_ARG, "logmel: tables missing from the handle");
@@ -215,7 +311,46 @@ int launch_logmel(const taste_weights_t& w, const float* wav, const int32_t* n_s
   TASTE_CUDA_OK(cudaMemsetAsync(scratch_max, 0, sizeof(unsigned int) * batch, stream));
   dim3 grid((TASTE_N_FRAMES + LM_FRAMES - 1) / LM_FRAMES, batch);
   const double feat_elems = double(batch) * TASTE_N_FRAMES * TASTE_N_MELS;
-  {
+  const bool tensor_dft = g_logmel_mode == 0 && w.dft_w_bf16 && scratch_planes && scratch_spectrum;
+  if (tensor_dft) {
+    const double plane_bytes = double(batch) * 2 * double(LOGMEL_PLANE) * 2;
+    const double spec_bytes = double(batch) * TASTE_N_FRAMES * TASTE_DFT_N * 4.0;
+    {
+      ProfScope ps(stream, KC_LOGMEL_SPLIT, double(batch) * double(LOGMEL_PLANE) * 4.0,
+                   double(batch) * TASTE_N_SAMPLES * 4.0 + plane_bytes);
+      dim3 g((unsigned)((LOGMEL_PLANE / 8 + 255) / 256), batch);
+      logmel_split_kernel<<<g, 256, 0, stream>>>(wav, n_samples, wav_stride, static_cast<__nv_bfloat16*>(scratch_planes));
+      TASTE_CUDA_OK(cudaGetLastError());
+    }
+    GemmDesc d;
+    d.a = scratch_planes;
+    d.k_inner = TASTE_DFT_K;
+    d.s_count = 2;                                     // s = 0: hi plane, 1: lo plane
+    d.rows_in = TASTE_N_FRAMES;
+    d.rows_out = TASTE_N_FRAMES;
+    d.batches = batch;
+    d.s_stride = LOGMEL_PLANE * 2;
+    d.r_stride = TASTE_HOP * 2;                        // overlapping frames: one hop per row
+    d.b_stride = 2 * LOGMEL_PLANE * 2;
+    d.taps = 3;                                        // K slabs hi(x) | hi(x) | lo(x)  against  hi(t) | lo(t) | hi(t)
+    d.tap_s[0] = 0, d.tap_s[1] = 0, d.tap_s[2] = 1;
+    d.w = w.dft_w_bf16;
+    d.n = TASTE_DFT_N;
+    d.out = scratch_spectrum;
+    d.ldc = TASTE_DFT_N;
+    d.epilogue = EPI_F32;
+    d.kclass = KC_LOGMEL_DFT;
+    // algorithmic bytes of the whole front-end: waveform in + features out (3.456 MB per utterance),
+    // booked on its dominant kernel; the helper passes are booked with their own reads + writes
+    d.alg_bytes = double(batch) * TASTE_N_SAMPLES * 4.0 + feat_elems * 4.0;
+    if (int rc = launch_gemm(d, stream)) return rc;
+    {
+      ProfScope ps(stream, KC_LOGMEL_MEL, double(batch) * TASTE_N_FRAMES * (3.0 * 201 + 2.0 * 394), spec_bytes + feat_elems * 4.0);
+      dim3 g((TASTE_N_FRAMES + MM_FRAMES - 1) / MM_FRAMES, batch);
+      logmel_mel_kernel<<<g, 256, 0, stream>>>(scratch_spectrum, w.mel_start, w.mel_count, w.mel_weight, logspec, scratch_max);
+      TASTE_CUDA_OK(cudaGetLastError());
+    }
+  } else {
     // algorithmic bytes of the whole front-end: waveform in + features out (3.456 MB per utterance),
     // booked on the tile kernel; the finish pass is booked with its own read + write
     ProfScope ps(stream, KC_LOGMEL_TILE, double(batch) * TASTE_N_FRAMES * (2.0 * 2 * 199 * 101 + 2.0 * 394),

@@ -69,6 +69,8 @@ class FrontendEngine:
         w.mel_start = self._dev("mel_start", st)
         w.mel_count = self._dev("mel_count", cnt)
         w.mel_weight = self._dev("mel_weight", wt)
+        wb = torch.from_numpy(mel.dft_gemm_weights().view("int16")).view(torch.bfloat16)
+        w.dft_w_bf16 = self._dev("dft_w_bf16", wb)
 
     def __del__(self):
         try:

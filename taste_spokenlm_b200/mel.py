@@ -67,6 +67,36 @@ def hann_periodic() -> np.ndarray:
     return (0.5 - 0.5 * np.cos(2.0 * np.pi * n / N_FFT)).astype(np.float32)
 
 
+DFT_K = 448      # TASTE_DFT_K
+DFT_N = 512      # TASTE_DFT_N
+
+
+def _bf16_round(x32: np.ndarray) -> np.ndarray:
+    """float32 -> nearest-even bf16, returned as float32 values."""
+    u = x32.astype(np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32)
+
+
+def dft_gemm_weights() -> np.ndarray:
+    """B operand of the tensor-core DFT: uint16 (bf16 bits) [DFT_N, 3 * DFT_K].
+
+    Row j is output column j of the GEMM: Re X[j] for j = 0..200, Im X[j - 256] (up to sign) for j = 256..456, zero
+    otherwise.  With t[j][n] = hann[n] * cos|sin(2 pi bin n / 400) in fp32 (n < 400; zero up to DFT_K), the three K slabs
+    are hi(t), lo(t), hi(t), to be multiplied with the frame slabs hi(x), hi(x), lo(x): x t ~= hi hi + hi lo + lo hi."""
+    n = np.arange(N_FFT, dtype=np.int64)[None, :]
+    k = np.arange(N_BINS, dtype=np.int64)[:, None]
+    ang = 2.0 * np.pi * ((n * k) % N_FFT).astype(np.float64) / N_FFT
+    win = hann_periodic().astype(np.float64)[None, :]
+    t = np.zeros((DFT_N, DFT_K), dtype=np.float32)
+    t[:N_BINS, :N_FFT] = (win * np.cos(ang)).astype(np.float32)
+    t[256:256 + N_BINS, :N_FFT] = (win * np.sin(ang)).astype(np.float32)
+    hi = _bf16_round(t)
+    lo = _bf16_round(t - hi)
+    w = np.concatenate([hi, lo, hi], axis=1)
+    return (w.view(np.uint32) >> 16).astype(np.uint16)
+
+
 def dft_tables():
     """cos/sin(2*pi*k*n/400) for n = 1..199 (row n-1; row 199 is zero) and k = 0..200, leading dim DFT_LD."""
     n = np.arange(1, 200, dtype=np.int64)[:, None]

@@ -279,7 +279,15 @@ def test_attention_ragged(lib, causal):
 # ---------------------------------------------------------------------------------------------------------------
 # log-mel front-end:  <= 1e-4 relative L2 (north star), checked against the oracle AND the reference fixtures
 # ---------------------------------------------------------------------------------------------------------------
-def test_logmel_vs_oracle_and_reference(lib, golden_dir):
+@pytest.fixture(params=[0, 1], ids=["tensor_dft", "fma_dft"])
+def logmel_mode(lib, request):
+    """Both formulations of the front-end DFT (taste_logmel_set_mode): split-bf16 GEMM on tcgen05, fp32 FMA kernel."""
+    assert lib.taste_logmel_set_mode(request.param) == 0
+    yield request.param
+    lib.taste_logmel_set_mode(0)
+
+
+def test_logmel_vs_oracle_and_reference(lib, golden_dir, logmel_mode):
     from taste_spokenlm_b200.frontend import WhisperFrontendB200
     fe = WhisperFrontendB200(whisper_model="large-v3", do_pad_trim=True, permute=True)
     z = np.load(os.path.join(golden_dir, "frontend.npz"))
@@ -295,7 +303,7 @@ def test_logmel_vs_oracle_and_reference(lib, golden_dir):
     assert torch.equal(feats, torch.full_like(feats, -1.5))                  # silence: every bin at the 1e-10 clamp
 
 
-def test_logmel_batch_ragged_and_bf16(lib):
+def test_logmel_batch_ragged_and_bf16(lib, logmel_mode):
     from taste_spokenlm_b200.engine import FrontendEngine
     eng = FrontendEngine("cuda:0")
     b = synth.synth_batch(3, [1.0, 30.0, 12.34, 0.01], [1, 1, 1, 1], pad_wave_to=480000)

@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     for name in declared:
         assert hasattr(built_lib, name), f"libtaste_b200.so does not export {name}"
     assert set(declared) == set(_lib._SIGS), "ctypes signature table out of sync with include/taste_b200.h"
-    assert built_lib.taste_abi_version() == 2
+    assert built_lib.taste_abi_version() == 3
     assert isinstance(built_lib.taste_launch_count(), int)
 
 
