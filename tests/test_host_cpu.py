@@ -118,6 +118,35 @@ def test_folded_dft_tables_reproduce_rfft():
     assert w[0] == 0.0
 
 
+def test_split_bf16_dft_weights_reproduce_the_oracle_logmel():
+    """The tensor-core front-end's arithmetic (logmel.cu mode 0) in numpy: frames split into bf16 halves against the
+    [512 x 1344] twiddle matrix {hi, lo, hi} of mel.dft_gemm_weights(), power, mel, log, floor, scale - must equal the
+    oracle's log-mel within the north star's 1e-4 relative L2 (the GPU test checks the kernels themselves)."""
+    W = mel.dft_gemm_weights()
+    assert W.shape == (mel.DFT_N, 3 * mel.DFT_K) and W.dtype == np.uint16
+    Wf = (W.astype(np.uint32) << 16).view(np.float32).astype(np.float64)
+    assert not Wf[201:256].any() and not Wf[457:].any() and not Wf[:, 400:448].any()      # padding rows / columns
+    n = 16000 * 3
+    wav = synth.synth_waveform(5, n)[None]
+    ref, _ = O.log_mel(wav, [n])
+    x = np.zeros(480000, np.float32)
+    x[:n] = wav[0].numpy()
+    xp = np.concatenate([np.pad(x, (200, 200), mode="reflect"), np.zeros(mel.DFT_K, np.float32)])
+    frames = xp[np.arange(3000)[:, None] * 160 + np.arange(mel.DFT_K)[None, :]]
+    hi = mel._bf16_round(frames)
+    lo = mel._bf16_round(frames - hi)
+    spec = (np.concatenate([hi, hi, lo], 1).astype(np.float64) @ Wf.T).astype(np.float32)
+    power = spec[:, :201] ** 2 + spec[:, 256:457] ** 2
+    st, cnt, wt = mel.sparse_filterbank()
+    M = np.zeros((128, 201), np.float32)
+    for m in range(128):
+        M[m, st[m]:st[m] + cnt[m]] = wt[m, :cnt[m]]
+    lg = np.log10(np.maximum(power @ M.T, 1e-10))
+    feats = (np.maximum(lg, lg.max() - 8.0) + 4.0) / 4.0
+    err = np.linalg.norm(feats - ref[0].numpy()) / np.linalg.norm(ref[0].numpy())
+    assert err < 1e-4, err
+
+
 def test_word_runs_padded_row_quirk():
     # SURVEY 8(a) R6: a final word with id 0 merges with the zero padding and is not pooled
     assert O.word_runs(torch.tensor([0, 0, 0, 0]), 2) == []
