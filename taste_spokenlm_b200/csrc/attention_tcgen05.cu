@@ -61,12 +61,14 @@ struct FaCfg {
   static_assert(kSmem <= 232448, "shared memory");
   static_assert((NT * 128 * kSoftmaxRegs + 128 * 40) <= 65536, "registers");
 };
-// VAR bits (template parameter; A/B knobs, see launch_attention_tcgen05): 4 = in-kernel timeline trace,
-// 64 = split phases: a row's MUFU pairs first, under the tile's ping-pong turn (one warp saturates the XU pipe), the
-// turn is handed over, then the polynomial pairs (FMA pipe) run under the other tile's MUFU phase; without it POLY of
-// every 16 pairs are interleaved and the turn is handed over after three of the four chunks,
-// 128 = speculative blocks: no row maximum after an item's first block (see the softmax loop), 256 = eight
-// row-maximum chains instead of four.
+// VAR bits (template parameter; A/B knobs, see launch_attention_tcgen05):
+//   4   in-kernel timeline trace (2 x 128 only)
+//   16  free-running tiles: no ping-pong turns between the softmax warpgroups (the default with 3 x 64)
+//   64  split phases: a row's MUFU pairs first, under the tile's turn (one warp saturates the XU pipe), the turn is
+//       handed over, then the polynomial pairs (FMA pipe) run under the next tile's MUFU phase; without it POLY of
+//       every 16 pairs are interleaved and the turn is handed over one chunk before the end of the row
+//   128 speculative blocks: no row maximum after an item's first block (see the softmax loop)
+//   256 eight row-maximum chains instead of four
 constexpr int FA_VAR_INTERLEAVED = 0;
 constexpr int FA_VAR_SPLIT = 64;
 constexpr int FA_VAR_SPEC = 64 | 128;
@@ -75,7 +77,6 @@ struct FaParams {
   long long* dbg;      // timeline trace (VAR bit 2 only)
   int q_len, kv_len;
   int heads, q_blocks, n_items;      // work item w = (b * heads + head) * q_blocks + qb
-  int fence[3];                      // all 1: opaque conditions that split the staged exp2 pass into basic blocks
 };
 
 // Work item w = (b * heads + head) * q_blocks + qb, walked with stride gridDim.x.  The stride is decomposed once; each
@@ -544,89 +545,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
           return sum0 + sum1;
         };
 
-        // Staged pass (VAR bit 3; split phases, 2 x 128 only).  ptxas places each MUFU pair's consumers (FADD2, F2FP) right
-        // behind the NEXT pair's MUFUs, i.e. ~16 issue cycles after the producer, but MUFU.EX2 results take ~40: the
-        // in-order warp stalls on every pair and the MUFU phase runs at ~30 cycles per pair instead of 16 (in-kernel
-        // timeline; XU pipe 55 % busy under the turn).  Here a chunk's 32 exponentials are issued back to back, in
-        // place, and consumed one stage later, next to the following chunk's exponentials; the stages sit in separate
-        // basic blocks (opaque always-true conditions), which the scheduler does not mix.
-        auto exp_pass_staged = [&](bool rescale, float alpha) {
-          static_assert(NC == 4 || !(VAR & 8), "staged pass: 2 x 128 geometry");
-          constexpr int kMu2 = kMuPairs - 32;               // MUFU pairs of chunk 2
-          bool o_ready = false;
-          if (j > 0) o_ready = mbar_try_wait(&o_full[i], uint32_t((g - 1) & 1));
-          const float neg_m = -m_used * kLog2e;
-          const uint64_t negm2 = f2_pack(neg_m, neg_m);
-          const uint64_t log2e2 = f2_pack(kLog2e, kLog2e);
-          uint64_t sum2 = f2_pack(0.f, 0.f);
-          auto mufu_pairs = [&](int c, int n) {             // r[c][0 .. 2n) <- 2^(...) in place
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              if (e < n) {
-                float t0, t1;
-                f2_unpack(f2_fma(f2_pack(__uint_as_float(r[c][2 * e]), __uint_as_float(r[c][2 * e + 1])), log2e2, negm2), t0, t1);
-                r[c][2 * e] = __float_as_uint(fast_exp2(t0));
-                r[c][2 * e + 1] = __float_as_uint(fast_exp2(t1));
-              }
-            }
-          };
-          auto consume_pairs = [&](int c, int n, uint32_t* pk) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              if (e < n) {
-                const float p0 = __uint_as_float(r[c][2 * e]), p1 = __uint_as_float(r[c][2 * e + 1]);
-                sum2 = f2_add(sum2, f2_pack(p0, p1));
-                pk[e] = pack_bf16x2(p0, p1);
-              }
-            }
-          };
-          uint32_t pk0[16], pk1[16], pk2[16], pk3[16];
-          if (p.fence[0]) mufu_pairs(0, 16);
-          if (p.fence[1]) {
-            mufu_pairs(1, 16);
-            consume_pairs(0, 16, pk0);
-          }
-          if (j > 0) {
-            // Only now is the previous block's P V needed: P_i has been consumed (it may be overwritten) and O_i is
-            // stable (it may be rescaled).
-            FA_TRACE(i, g * 8 + 4);
-            if (!o_ready) mbar_wait(&o_full[i], uint32_t((g - 1) & 1));
-            FA_TRACE(i, g * 8 + 5);
-            tc_fence_after();
-            if (rescale) rescale_o(alpha);
-          }
-          tmem_st_32x32b_x16(t_p, pk0);
-          if (p.fence[2]) {
-            mufu_pairs(2, kMu2);
-            consume_pairs(1, 16, pk1);
-          }
-          tmem_st_32x32b_x16(t_p + 16, pk1);
-          turn_pass(g);                                     // MUFU phase over: the next tile's turn
-          consume_pairs(2, kMu2, pk2);
-#pragma unroll
-          for (int e = kMu2; e < 16; ++e) {
-            const uint64_t t2 = f2_fma(f2_pack(__uint_as_float(r[2][2 * e]), __uint_as_float(r[2][2 * e + 1])), log2e2, negm2);
-            float p0, p1;
-            exp2_poly2(t2, p0, p1);
-            sum2 = f2_add(sum2, f2_pack(p0, p1));
-            pk2[e] = pack_bf16x2(p0, p1);
-          }
-          tmem_st_32x32b_x16(t_p + 32, pk2);
-          s_ready = (g + 1 < total_g) && mbar_try_wait(&s_full[i], uint32_t((g + 1) & 1));
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const uint64_t t2 = f2_fma(f2_pack(__uint_as_float(r[3][2 * e]), __uint_as_float(r[3][2 * e + 1])), log2e2, negm2);
-            float p0, p1;
-            exp2_poly2(t2, p0, p1);
-            sum2 = f2_add(sum2, f2_pack(p0, p1));
-            pk3[e] = pack_bf16x2(p0, p1);
-          }
-          tmem_st_32x32b_x16(t_p + 48, pk3);
-          float sum0, sum1;
-          f2_unpack(sum2, sum0, sum1);
-          return sum0 + sum1;
-        };
-
         // Speculative mode (VAR bit 7): only the first block of an item computes its row maximum.  Later blocks
         // exponentiate against the stale reference straight away - fp32 / bf16 carry 2^(+-126), so a reference that
         // is too low costs no accuracy - and a row whose block sum shows that an argument came near the fp32 range
@@ -645,9 +563,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
         // lock-step, where both warps of a scheduler fight for the MUFU queue and neither feeds the FMA pipe; the other
         // tile's TMEM loads, row maximum and waits run under this tile's exponentials.
         turn_wait();
-        float bsum;
-        if constexpr ((VAR & 8) != 0) bsum = exp_pass_staged(any_grow, alpha);
-        else bsum = exp_pass(std::true_type{}, any_grow, alpha);
+        float bsum = exp_pass(std::true_type{}, any_grow, alpha);
         if constexpr (kSpec) {
           if (!exact) {
             const bool bad = !(bsum < 1.0e30f);            // also catches inf and NaN
@@ -727,7 +643,7 @@ int launch_attention_tcgen05(const AttnDesc& d, cudaStream_t stream) {
   X(FA_VAR_FREE | 128, 6, 3, 64) X(FA_VAR_SPLIT, 5, 2, 64)                                                      \
   X(FA_VAR_SPLIT, 5, 2, 128) X(FA_VAR_SPLIT, 6, 2, 128) X(FA_VAR_SPLIT | 4, 5, 2, 128)                          \
   X(FA_VAR_SPLIT | 256, 5, 2, 128) X(FA_VAR_INTERLEAVED, 6, 2, 128) X(FA_VAR_INTERLEAVED, 0, 2, 128)            \
-  X(FA_VAR_SPEC, 5, 2, 128) X(FA_VAR_SPEC | 4, 5, 2, 128) X(FA_VAR_SPLIT | 8, 5, 2, 128)                        \
+  X(FA_VAR_SPEC, 5, 2, 128) X(FA_VAR_SPEC | 4, 5, 2, 128)                                                       \
   X(FA_VAR_SPLIT | 16, 5, 2, 128) X(FA_VAR_INTERLEAVED | 16, 6, 2, 128)
   static bool configured = false;
   if (!configured) {
@@ -764,7 +680,6 @@ int launch_attention_tcgen05(const AttnDesc& d, cudaStream_t stream) {
   p.q_len = d.q_len;
   p.kv_len = d.kv_len;
   p.heads = d.heads;
-  p.fence[0] = p.fence[1] = p.fence[2] = 1;
   p.q_blocks = (d.q_len + want_nt * FA_BQ - 1) / (want_nt * FA_BQ);
   p.n_items = p.q_blocks * d.heads * d.batch;
   static int n_sm = 0;

@@ -214,11 +214,13 @@ logmel_split_kernel(const float* __restrict__ wav, const int32_t* __restrict__ n
 
 // spectrum [b * 3000 + f][TASTE_DFT_N] (Re at column k, Im at 256 + k) -> power -> mel -> log10 -> logspec, running max.
 constexpr int MM_FRAMES = 32;
+constexpr int MM_LDL = TASTE_N_MELS + 1;      // log tile stride (odd)
 __global__ void __launch_bounds__(256)
 logmel_mel_kernel(const float* __restrict__ spectrum, const int32_t* __restrict__ mel_start,
                   const int32_t* __restrict__ mel_count, const float* __restrict__ mel_weight,
                   float* __restrict__ logspec, unsigned int* __restrict__ umax) {
   __shared__ float sP[MM_FRAMES * LM_LDP];
+  __shared__ float sL[MM_FRAMES * MM_LDL];
   __shared__ float s_red[8];
   const int b = blockIdx.y;
   const int f0 = blockIdx.x * MM_FRAMES;
@@ -241,22 +243,29 @@ logmel_mel_kernel(const float* __restrict__ spectrum, const int32_t* __restrict_
     }
   }
   __syncthreads();
+  // mel projection with lane = frame (power-tile stride 209 is odd: conflict-free) and 16 filters per warp (start,
+  // count and weights are warp-uniform: broadcast loads, no divergence); the log values go through shared memory so
+  // that the global stores are coalesced along the mel axis.  (With lane = filter the scattered power-tile reads
+  // made this phase shared-memory-bound.)
   float lmax = -INFINITY;
-  const int m = tid & 127;
-  const int ms = __ldg(mel_start + m);
-  const int mc = __ldg(mel_count + m);
-  float wgt[TASTE_MEL_MAXW];
-#pragma unroll
-  for (int j = 0; j < TASTE_MEL_MAXW; ++j) wgt[j] = __ldg(mel_weight + m * TASTE_MEL_MAXW + j);
-  for (int f = tid >> 7; f < MM_FRAMES; f += 2) {
-    if (f0 + f >= TASTE_N_FRAMES) break;
+  const int warp = tid >> 5;
+  const bool frame_ok = f0 + lane < TASTE_N_FRAMES;
+#pragma unroll 4
+  for (int mm = 0; mm < 16; ++mm) {
+    const int m = warp * 16 + mm;
+    const int ms = __ldg(mel_start + m);
+    const int mc = __ldg(mel_count + m);
+    const float* pw = sP + lane * LM_LDP + ms;
     float acc = 0.f;
-#pragma unroll
-    for (int j = 0; j < TASTE_MEL_MAXW; ++j)
-      if (j < mc) acc = fmaf(wgt[j], sP[f * LM_LDP + ms + j], acc);
+    for (int j = 0; j < mc; ++j) acc = fmaf(__ldg(mel_weight + m * TASTE_MEL_MAXW + j), pw[j], acc);
     const float lg = log10f(fmaxf(acc, 1e-10f));
-    logspec[(int64_t(b) * TASTE_N_FRAMES + f0 + f) * TASTE_N_MELS + m] = lg;
-    lmax = fmaxf(lmax, lg);
+    sL[lane * MM_LDL + m] = lg;
+    if (frame_ok) lmax = fmaxf(lmax, lg);
+  }
+  __syncthreads();
+  for (int idx = tid; idx < MM_FRAMES * TASTE_N_MELS; idx += 256) {
+    const int f = idx >> 7, m = idx & 127;
+    if (f0 + f < TASTE_N_FRAMES) logspec[(int64_t(b) * TASTE_N_FRAMES + f0 + f) * TASTE_N_MELS + m] = sL[f * MM_LDL + m];
   }
   lmax = warp_max(lmax);
   if (lane == 0) s_red[tid >> 5] = lmax;
