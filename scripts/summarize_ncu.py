@@ -15,7 +15,7 @@ def launches():
         k = (row["Kernel Name"].split("(")[0][:70], row["Grid Size"], row["Block Size"])
         a = agg.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += v; tot += v
     out = [f"# ncu launch list of ONE bench step (batch 64 x 30 s): gpu__time_duration per launch, cold-cache and serialised\n"
-           f"# command: ncu --metrics gpu__time_duration.sum --clock-control none -k <our kernels> -s 684 -c 228 python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline\n"
+           f"# command: ncu --metrics gpu__time_duration.sum --clock-control none -k <our kernels> -s 690 -c 230 python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline\n"
            f"# total {tot:.2f} ms over {sum(a[0] for a in agg.values())} launches\n"]
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         out.append(f"{a[1]:9.3f} ms {100*a[1]/tot:5.1f}%  {a[0]:4d}x  avg {a[1]/a[0]:8.4f} ms  {k[0]}  grid={k[1]} block={k[2]}")
