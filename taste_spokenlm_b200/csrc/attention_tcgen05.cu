@@ -689,7 +689,12 @@ int launch_attention_tcgen05(const AttnDesc& d, cudaStream_t stream) {
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     if (n_sm <= 0) n_sm = 148;
   }
-  dim3 grid(p.n_items < n_sm ? p.n_items : n_sm);
+  int n_cta = p.n_items < n_sm ? p.n_items : n_sm;
+  if (const char* lim = getenv("TASTE_FA_MAX_CTAS")) {         // co-scheduling probe (scripts/coschedule_probe.py)
+    const int v = atoi(lim);
+    if (v > 0 && v < n_cta) n_cta = v;
+  }
+  dim3 grid(n_cta);
   const double pairs = double(d.batch) * d.q_len * d.kv_len;
   ProfScope ps(stream, d.kclass == KC_ATTN_ENC ? KC_ATTN_ENC : KC_ATTN_TC, 4.0 * pairs * FA_HD * d.heads,
                2.0 * FA_HD * d.heads * double(d.batch) * (2.0 * d.q_len + 2.0 * d.kv_len));

@@ -698,7 +698,11 @@ static int launch_cfg2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     max_pairs = n;
     if (getenv("TASTE_DEBUG")) fprintf(stderr, "[taste] gemm pair kernel: %d co-resident CTA pairs\n", n);
   }
-  const int pairs = p.total_tiles < max_pairs ? p.total_tiles : max_pairs;
+  int pairs = p.total_tiles < max_pairs ? p.total_tiles : max_pairs;
+  if (const char* lim = getenv("TASTE_GEMM_MAX_PAIRS")) {      // co-scheduling probe (scripts/coschedule_probe.py)
+    const int v = atoi(lim);
+    if (v > 0 && v < pairs) pairs = v;
+  }
   const double m = double(p.rows_out) * (p.total_tiles / (p.n_tiles * p.m_tiles_per_batch));
   const double n = double(p.n_tiles) * BN2, k = double(p.taps) * p.kb_per_tap * BK;
   const double out_b = (EPI == EPI_BF16 || EPI == EPI_GELU_BF16) ? 2.0 : (EPI == EPI_RESID_F32 ? 8.0 : 4.0);
