@@ -29,6 +29,9 @@ def test_argument_errors_without_a_gpu(built_lib):
     assert b"null" in built_lib.taste_last_error()
     assert built_lib.taste_gemm_bf16(None, None, None, None, 1, 128, 64, 9, None) == -1
     assert built_lib.taste_ws_bytes(None, 4, 100) == 0
+    assert built_lib.taste_logmel_set_mode(2) == -1 and b"logmel_set_mode" in built_lib.taste_last_error()
+    assert built_lib.taste_logmel_set_mode(0) == 0
+    assert built_lib.taste_logmel_f32(None, None, None, 1, 0, None, None, None, 0, None) == -1
 
 
 def test_tower_module_state_layout_matches_reference_keys():
