@@ -167,13 +167,13 @@ def build_reference_tower(d_model=1280, enc_layers=32, dec_layers=2, heads=20, f
     return tower.eval()
 
 
-def _RefTower(JES, AQ, **kw):
-    """Instantiate the reference's own `TasteAudioTower` class.
+def import_modeling_taste():
+    """Import the reference's `taste_speech/modeling_taste.py` where it lies.
 
-    `taste_speech/modeling_taste.py` imports the whole spoken-LM stack at module top; only its
-    `TasteAudioTower` class is needed, so the module is executed with the unrelated imports stubbed.
+    The module imports the whole spoken-LM stack at its top; only `TasteAudioTower` / `TasteForCausalLM`'s class
+    bodies are needed here, so the unrelated sub-modules (speech decoder, bridge, sampler ...) are stubbed.
     """
-    import torch
+    install()
     name = "taste_speech.modeling_taste"
     if name not in sys.modules:
         for sub, attrs in (
@@ -190,7 +190,28 @@ def _RefTower(JES, AQ, **kw):
             if sub not in sys.modules:
                 _stub(sub, **attrs)
         importlib.import_module(name)
-    MT = sys.modules[name]
+    return sys.modules[name]
+
+
+def import_processing_taste():
+    """Import the reference's `taste_speech/processing_taste.py` (binds `WhisperFrontend` at PT:20); the vocoder side
+    it also imports (`inference_audio`, omegaconf) is stubbed."""
+    install()
+    name = "taste_speech.processing_taste"
+    if name not in sys.modules:
+        if "taste_speech.modules_taste.inference_audio" not in sys.modules:
+            _stub("taste_speech.modules_taste.inference_audio", VoiceGenerator=object)
+        try:
+            import omegaconf  # noqa: F401
+        except ImportError:
+            _stub("omegaconf", DictConfig=dict)
+        importlib.import_module(name)
+    return sys.modules[name]
+
+
+def _RefTower(JES, AQ, **kw):
+    """Instantiate the reference's own `TasteAudioTower` class (MT:33-95)."""
+    MT = import_modeling_taste()
     return MT.TasteAudioTower(is_joint_encoder_segmenter=True, quantization_on=True, **kw)
 
 

@@ -21,10 +21,27 @@ PREFIX = (50258, 50259, 50360, 50364)     # MT:147
 EOS = 50257                               # MT:149
 
 
+def _on_device(fn):
+    """Make the engine's device current around a C-ABI call: the library caches per-device state (shared-memory
+    attributes, SM count) for the CURRENT device and launches on the stream handed in, so a tower on cuda:1 must not be
+    driven while cuda:0 is current."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        if torch.cuda.current_device() == self.device.index:
+            return fn(self, *a, **k)
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+    return wrapped
+
+
 def _require_cuda(device) -> torch.device:
     device = torch.device(device)
     if device.type != "cuda" or not torch.cuda.is_available():
         raise _lib.TasteError("the TASTE B200 path needs a CUDA device (sm_100a); there is no CPU fallback")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
     return device
 
 
@@ -80,6 +97,7 @@ class FrontendEngine:
         except Exception:
             pass
 
+    @_on_device
     def logmel(self, wav: torch.Tensor, n_samples: torch.Tensor, want_f32: bool = True, want_bf16: bool = False):
         """wav fp32 [B, stride] on device; n_samples int32 [B] on device.  Returns (feats_f32|None, feats_bf16|None)."""
         assert wav.is_cuda and wav.dtype == torch.float32 and wav.dim() == 2 and wav.stride(1) == 1
@@ -111,6 +129,7 @@ class TowerEngine(FrontendEngine):
             raise _lib.TasteError("d_model == codebook_dim (identity RVQ projections) is not supported")
 
     # ---- packing ---------------------------------------------------------------------------------------------
+    @_on_device
     def pack(self, sd: Mapping[str, torch.Tensor]) -> None:
         """(Re)build the kernel-side weight set from a state_dict with the reference's key names."""
         cfg, dev = self.cfg, self.device
@@ -244,6 +263,7 @@ class TowerEngine(FrontendEngine):
         return self.ws.get(self.lib.taste_ws_bytes(self.handle, batch, sum_tokens))
 
     # ---- stages ----------------------------------------------------------------------------------------------
+    @_on_device
     def encode(self, feats: torch.Tensor):
         """feats [B,3000,128] fp32 or bf16 on device -> (h_last, h_target) bf16 [B,1500,D].   JES:133-223"""
         B, D = feats.shape[0], self.cfg.d_model
@@ -273,6 +293,7 @@ class TowerEngine(FrontendEngine):
         cu[1:] = np.cumsum([len(r) for r in rows])
         return np.concatenate(rows).astype(np.int32), cu
 
+    @_on_device
     def aggregate(self, h_last, h_t, tokens_packed: torch.Tensor, cu_tokens: torch.Tensor, sum_tokens: int,
                   max_tokens: int) -> torch.Tensor:
         """-> decoder final-LN states fp32 [sum_tokens, D].   CW:1200-1437 with dict K/V (JES:377-388)"""
@@ -284,6 +305,7 @@ class TowerEngine(FrontendEngine):
                                                  _lib.ptr(ws), ws.numel(), self._stream()), "taste_aggregator_fwd")
         return out
 
+    @_on_device
     def word_pool(self, dec_out, cu_tokens, word_ids, lengths, B, Tmax) -> torch.Tensor:
         z = torch.empty(B, Tmax, self.cfg.d_model, dtype=torch.float32, device=dec_out.device)
         _lib.check(self.lib.taste_word_pool_f32(_lib.ptr(dec_out), _lib.ptr(cu_tokens), _lib.ptr(word_ids),
@@ -291,6 +313,7 @@ class TowerEngine(FrontendEngine):
                                                 self._stream()), "taste_word_pool_f32")
         return z
 
+    @_on_device
     def rvq_encode(self, z: torch.Tensor, lengths: Optional[torch.Tensor], want_quantized: bool = True):
         """z fp32 [B,T,in_dim] -> (quantized [B,T,D] | None, indices int64 [B,T,Q]).   RVQ:359-490 / RVQ:258-357"""
         assert z.is_cuda and z.dtype == torch.float32 and z.is_contiguous() and z.dim() == 3
@@ -301,6 +324,7 @@ class TowerEngine(FrontendEngine):
                                                  _lib.ptr(idx), _lib.ptr(qz), self._stream()), "taste_rvq_encode_f32")
         return qz, idx
 
+    @_on_device
     def rvq_decode(self, indices: torch.Tensor, project_out: bool = True) -> torch.Tensor:
         assert indices.is_cuda and indices.dtype == torch.int64
         shape = indices.shape[:-1]
@@ -311,6 +335,7 @@ class TowerEngine(FrontendEngine):
                                                  _lib.ptr(out), self._stream()), "taste_rvq_decode_f32")
         return out.reshape(*shape, out.shape[-1])
 
+    @_on_device
     def map_to_llm_tokens(self, asr_indices, asr_word_ids, asr_token_lengths, llm_word_ids, llm_token_lengths):
         """extract_vq epilogue (MT:1438-1450, MT:1877-1881): asr-token indices [B,T,Q] -> llm-token indices [B,L,Q]
         (-1 where an llm token is not the first token of a word that also starts an asr word)."""
@@ -328,6 +353,7 @@ class TowerEngine(FrontendEngine):
                    "taste_map_to_llm_tokens")
         return out
 
+    @_on_device
     def assemble_tokens(self, ids_dev: torch.Tensor, lens32: torch.Tensor, cu: torch.Tensor, sum_tokens: int):
         """Packed assembled ids on the device (MT:144-152); see taste_assemble_tokens."""
         B, Tmax = ids_dev.shape

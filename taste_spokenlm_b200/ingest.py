@@ -136,11 +136,25 @@ class ResampleMeanB200:
         return tb
 
     def _staging(self, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
-        if self._pinned is None or self._pinned.numel() < n:
+        """Two pinned / device staging pairs used in rotation.  The H2D copy is asynchronous, so before the host writes
+        a pinned buffer again it waits for the event recorded after that buffer's previous copy; the device buffer is
+        protected by stream order (copy and kernel are issued on the same stream).  With two pairs the host packs
+        batch i + 1 while batch i is still in flight."""
+        self._slot = (getattr(self, "_slot", -1) + 1) % 2
+        if not hasattr(self, "_slots"):
+            self._slots = [None, None]
+        st = self._slots[self._slot]
+        if st is None or st[0].numel() < n:
+            if st is not None and st[2] is not None:
+                st[2].synchronize()
             cap = max(n, 1 << 20)
-            self._pinned = torch.empty(cap, dtype=torch.float32).pin_memory()
-            self._dev_in = torch.empty(cap, dtype=torch.float32, device=self.device)
-        return self._pinned, self._dev_in
+            st = [torch.empty(cap, dtype=torch.float32).pin_memory(),
+                  torch.empty(cap, dtype=torch.float32, device=self.device), None]
+            self._slots[self._slot] = st
+        if st[2] is not None:
+            st[2].synchronize()               # the previous DMA out of this pinned buffer has finished
+        self._pinned, self._dev_in = st[0], st[1]
+        return st[0], st[1]
 
     def output_lengths(self, n_in: Sequence[int], orig_freq: int) -> np.ndarray:
         tb = self.tables(orig_freq)
@@ -186,6 +200,9 @@ class ResampleMeanB200:
         for a, o in zip(arrs, offsets[:-1]):
             host[o: o + a.size] = a.reshape(-1)
         dev_in[:total].copy_(pinned[:total], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._slots[self._slot][2] = ev
         return self.run_device(dev_in, offsets, channels, n_in, orig_freq, out=out)
 
 

@@ -185,6 +185,37 @@ def random_weights(cfg: TowerConfig, seed: int = 1234, only=None) -> Dict[str, t
     return out
 
 
+def default_init_weights(cfg: TowerConfig, seed: int = 1234) -> Dict[str, torch.Tensor]:
+    """The second weight set of SURVEY.md §7 hard part 3: what the reference's constructors leave behind without a
+    checkpoint.  HF Whisper `_init_weights` (Linear / Conv1d / Embedding ~ N(0, 0.02^2), biases 0, LayerNorm 1 / 0,
+    sinusoidal encoder positions), identity cross-attention v_proj (JES:320-322), torch's default Linear init for
+    `project_in` / `project_out` (U(+-1/sqrt(fan_in))), N(0,1) codebooks marked initted.  Ill-conditioned on purpose:
+    only a handful of codes are in play, so index agreement on it is REPORTED, never asserted."""
+    out: Dict[str, torch.Tensor] = OrderedDict()
+    for key, shape in state_dict_spec(cfg).items():
+        if key.endswith("embed_positions.weight") and key.startswith(ENC):
+            r = sinusoids(shape[0], shape[1])
+        elif key.endswith("_codebook.initted") or key.endswith("_codebook.cluster_size"):
+            r = torch.ones(shape)
+        elif key.endswith("_codebook.embed") or key.endswith("_codebook.embed_avg"):
+            r = _randn(key.replace("embed_avg", "embed"), shape, seed)
+        elif "layer_norm" in key:
+            r = torch.ones(shape) if key.endswith("weight") else torch.zeros(shape)
+        elif key.endswith("encoder_attn.v_proj.weight"):
+            r = torch.eye(shape[0])
+        elif key.startswith(RVQ):
+            fan_in = shape[1] if len(shape) > 1 else {"project_in.bias": cfg.d_model, "project_out.bias": cfg.codebook_dim}.get(
+                key[len(RVQ):], cfg.codebook_dim)
+            g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(key.encode())) & 0x7FFFFFFFFFFFFFFF)
+            r = (torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(fan_in)
+        elif key.endswith(".bias"):
+            r = torch.zeros(shape)
+        else:
+            r = 0.02 * _randn(key, shape, seed)
+        out[key] = r.contiguous()
+    return out
+
+
 def synth_waveform(seed: int, n_samples: int, total: int = None) -> torch.Tensor:
     """Deterministic speech-like test signal: 8 amplitude-modulated sinusoids 80-7600 Hz + white noise."""
     g = torch.Generator(device="cpu")

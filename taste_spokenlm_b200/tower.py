@@ -196,7 +196,7 @@ class ResidualVQB200(nn.Module):
         self.project_out = nn.Linear(codebook_dim, dim) if self.has_projections else nn.Identity()
         self.layers = nn.ModuleList([_VQLayer(codebook_size, codebook_dim, kmeans_init) for _ in range(num_quantizers)])
         self.mlps = nn.ModuleList([_UnusedMLP(codebook_dim) for _ in range(num_quantizers - 1)])
-        self._engine_ref = None          # set by the owning tower (not a submodule: avoids a reference cycle in state)
+        self._tower_ref = None           # weak reference to the owning TasteAudioTowerB200 (set in its constructor)
 
     @property
     def codebook_size(self):
@@ -211,9 +211,14 @@ class ResidualVQB200(nn.Module):
         return torch.stack([l._codebook.embed[0] for l in self.layers], dim=0)
 
     def _engine(self) -> TowerEngine:
-        if self._engine_ref is None:
-            raise _lib.TasteError("ResidualVQB200 is not attached to a tower engine")
-        return self._engine_ref()
+        """The owning tower's engine, resolved on EVERY call: packing is lazy (the spoken-LM side calls
+        `get_output_from_indices` etc. with no tower forward in the process, MT:681-689, 884-904, bridge.py:413) and
+        follows the tower's state key, so codebooks loaded or moved after the first forward are never stale."""
+        tower = self._tower_ref() if self._tower_ref is not None else None
+        if tower is None:
+            raise _lib.TasteError("ResidualVQB200 is not attached to a TasteAudioTowerB200 (the kernels' packed "
+                                  "codebooks live in the tower's engine)")
+        return tower.engine()
 
     def _check_initted(self):
         for l in self.layers:                                            # VQ:349-351 would run k-means here
@@ -321,8 +326,13 @@ class TasteAudioTowerB200(nn.Module):
         self.add_eos = True
         import weakref
         self.audio_joint_encoder_segmenter._tower_ref = weakref.ref(self)
+        if self.quantization_on:
+            self.vq.rvq._tower_ref = weakref.ref(self)
         self._engine: Optional[TowerEngine] = None
         self._engine_key = None
+        self._state_epoch = 0
+        self._sentinels = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_engine())
 
     # ---- construction helpers ----
     @classmethod
@@ -349,26 +359,46 @@ class TasteAudioTowerB200(nn.Module):
         self.load_state_dict(converted, strict=True)
 
     # ---- engine management ----
+    def invalidate_engine(self) -> None:
+        """Forget the packed kernel-side weights (they are rebuilt on the next call).  Called automatically after
+        `load_state_dict` and `.to()` / `.cuda()` / `.float()`; call it by hand after mutating a parameter in place
+        through a view the sentinel check below cannot see."""
+        self._state_epoch += 1
+
+    def _apply(self, fn, *a, **k):                                       # .to / .cuda / .cpu / dtype casts
+        r = super()._apply(fn, *a, **k)
+        self._state_epoch = getattr(self, "_state_epoch", 0) + 1
+        self._sentinels = None
+        return r
+
     def _state_key(self):
+        """O(1) in the number of tensors: an epoch bumped by the hooks above, plus storage + version of a few sentinel
+        tensors (first / last encoder weights, decoder embedding, RVQ projection and codebooks) so that in-place edits
+        of the usual suspects (`copy_`, k-means re-init, optimizer steps on the whole module) are seen as well.  Walking
+        all ~700 tensors on every forward cost 5 % of the B = 1 latency."""
+        if self._sentinels is None:
+            named = dict(self.named_parameters())
+            named.update(dict(self.named_buffers()))
+            keys = list(named)
+            pick = [keys[0], keys[len(keys) // 2], keys[-1]] + [k for k in keys if k.endswith("_codebook.embed")
+                                                                  or k.endswith("project_in.weight")
+                                                                  or k.endswith("embed_tokens.weight")]
+            self._sentinels = [named[k] for k in dict.fromkeys(pick)]
         ver = 0
         ptr = 0
-        for t in list(self.parameters()) + list(self.buffers()):
+        for t in self._sentinels:
             ver += t._version
             ptr ^= t.data_ptr()
-        dev = next(self.parameters()).device
-        return (str(dev), ver, ptr)
+        return (self._state_epoch, str(self._sentinels[0].device), ver, ptr)
 
     def engine(self) -> TowerEngine:
-        """Packed kernel-side weights; rebuilt when any parameter/buffer changed (version counter or storage)."""
+        """Packed kernel-side weights; rebuilt when the state changed (see `_state_key`)."""
         key = self._state_key()
         if self._engine is None or key != self._engine_key:
             dev = next(self.parameters()).device
             eng = TowerEngine(self.cfg, dev)
             eng.pack(self.state_dict())
             self._engine, self._engine_key = eng, key
-            if self.quantization_on:
-                import weakref
-                self.vq.rvq._engine_ref = weakref.ref(eng)
         return self._engine
 
     # ---- MT:108-211 ----

@@ -71,6 +71,67 @@ def tower_case(name, cfg_name, wseed, bseed, durs, toks, fe):
     print(name, "ok", tuple(out["quantized_indices"].shape))
 
 
+# FULL-geometry parity fixtures with >= 2000 tokens: 28 fixed-length 30 s x 64-token utterances
+# (config 2's shape) + 6 ragged ones.  ~10 min of CPU in the build container for the conditioned weight set.
+BIG_RAGGED = [(5.0, 14), (12.0, 32), (20.0, 54), (27.3, 74), (8.1, 22), (29.9, 80)]
+BIG_CASES = {
+    # name: (weight init, weight seed, batch seed, durations, tokens)
+    "tower_full_b34": ("conditioned", 1234, 11, [30.0] * 28 + [d for d, _ in BIG_RAGGED], [64] * 28 + [t for _, t in BIG_RAGGED]),
+    # SURVEY §7 hard part 3: the default HF init (std 0.02) is REPORTED, not asserted (ill-conditioned: ~4 codes in play)
+    "tower_full_default_init": ("hf_default", 1234, 12, [30.0] * 6 + [11.0, 21.5], [64] * 6 + [30, 58]),
+}
+
+
+def tower_big_case(name, init, wseed, bseed, durs, toks, fe):
+    cfg = synth.FULL
+    tower = ref_shim.build_reference_tower()
+    W = synth.random_weights(cfg, wseed) if init == "conditioned" else synth.default_init_weights(cfg, wseed)
+    tower.load_state_dict(W, strict=True)
+    batch = synth.synth_batch(bseed, durs, toks)
+    B = len(durs)
+    residuals = [[] for _ in range(cfg.num_quantizers)]
+    hooks = [layer.register_forward_pre_hook(lambda m, a, q=q: residuals[q].append(a[0].detach().clone()))
+             for q, layer in enumerate(tower.vq.rvq.layers)]
+    outs, aggs, hl, ht = [], [], [], []
+    # ONE reference forward over the whole batch (~20 GB of eager attention scores at B = 34); the aggregator output and the encoder states are captured by hooks on the
+    # reference's own sub-modules (input of `tower.vq`, MT:178-181; output of the encoder wrapper, JES:133-223)
+    hooks.append(tower.vq.register_forward_pre_hook(lambda m, a: aggs.append(a[0].detach().clone())))
+
+    def enc_hook(m, a, out):
+        e = out["encoded_feats"]
+        hl.append(e["last_hidden"][:, ::100, ::8].clone()); ht.append(e["6"][:, ::100, ::8].clone())
+    hooks.append(tower.audio_joint_encoder_segmenter.audio_encoder.register_forward_hook(enc_hook))
+    feats = ref_frontend(fe, batch["wav"], batch["n_samples"])
+    outs.append(tower(batch["asr_token_ids"], batch["asr_token_lengths"], feats, torch.tensor([3000] * B),
+                      asr_word_ids=batch["asr_word_ids"]))
+    for h in hooks:
+        h.remove()
+    Tm = max(toks)
+    def padT(x, fill=0):
+        if x.shape[1] == Tm:
+            return x
+        pad = torch.full((x.shape[0], Tm - x.shape[1]) + tuple(x.shape[2:]), fill, dtype=x.dtype)
+        return torch.cat([x, pad], 1)
+    idx = torch.cat([padT(o["quantized_indices"], -1) for o in outs])
+    agg = torch.cat([padT(a) for a in aggs])
+    assert len(aggs) == len(outs) == len(hl)
+    lens = torch.cat([o["audio_unit_lengths"] for o in outs])
+    valid = torch.arange(Tm)[None] < lens[:, None]
+    # residual entering each RVQ level, as the reference's own VectorQuantize layers received it
+    res = torch.stack([torch.cat([padT(r) for r in residuals[q]]) for q in range(cfg.num_quantizers)], 2)   # [B,Tm,Q,dc]
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"),
+        meta=json.dumps(dict(config="FULL", init=init, weight_seed=wseed, batch_seed=bseed, durations=durs, tokens=toks,
+                             chan_stride=8)),
+        h_last_sub=torch.cat(hl).numpy(), h_target_sub=torch.cat(ht).numpy(),
+        aggregated_packed=agg[valid].numpy(),                      # [sum T, 1280] fp32, valid tokens in (b, t) order
+        residuals_packed=res[valid].numpy(),                       # [sum T, Q, 256] fp32
+        audio_unit_lengths=lens.numpy(),
+        quantized_indices=idx.numpy().astype(np.int16),
+    )
+    print(name, "ok", tuple(idx.shape), int(valid.sum()), "tokens")
+
+
 def frontend_cases(fe):
     specs = [("1s", 16000), ("10s", 160000), ("29.99s", 479840), ("30s", 480000), ("33s_trimmed", 528000),
              ("odd", 123457)]
@@ -213,6 +274,8 @@ if __name__ == "__main__":
     for name in which:
         if name in CASES:
             tower_case(name, *CASES[name], fe)
+        if name in BIG_CASES:                    # only on request: minutes of CPU each
+            tower_big_case(name, *BIG_CASES[name], fe)
     if "frontend" in which:
         frontend_cases(fe)
     if "ingest" in which:

@@ -69,6 +69,28 @@ def test_resample_ragged_batch_vs_oracle(built_lib, sr):
         assert np.all(got[m:] == 7.0)                                  # nothing written past the utterance
 
 
+def test_resample_back_to_back_calls_do_not_share_live_staging(built_lib):
+    """the H2D copy out of the pinned staging buffer is asynchronous; many large back-to-back calls (the
+    mixed-sampling-rate loop of CorpusIngestB200.tokenize_batch) must not let the host overwrite a buffer a DMA is still
+    reading.  Every call's output is checked against the same call made alone after a full synchronize."""
+    rs = ingest.ResampleMeanB200("cuda:0")
+    groups = [(24000, [synth.synth_pcm(1200 + i, 700000, 1) for i in range(6)]),
+              (44100, [synth.synth_pcm(1300 + i, 1300000, 1) for i in range(6)]),
+              (8000, [synth.synth_pcm(1400 + i, 240000, 2) for i in range(6)]),
+              (48000, [synth.synth_pcm(1500 + i, 1400000, 1) for i in range(6)])]
+    outs = []
+    for rate, arrs in groups * 2:                                  # 8 calls with no synchronisation in between
+        w, ns = rs(arrs, rate)
+        outs.append((w.clone(), ns.clone()))
+    torch.cuda.synchronize()
+    for k, (rate, arrs) in enumerate(groups * 2):
+        torch.cuda.synchronize()
+        w, ns = rs(arrs, rate)
+        torch.cuda.synchronize()
+        assert torch.equal(ns, outs[k][1])
+        assert torch.equal(w, outs[k][0]), (k, rate)
+
+
 def test_resample_properties_full_size(resampler):
     """Batch 64 x 30 s at 24 kHz (the Emilia rate): linearity, channel-mean consistency, pass-band gain."""
     B, n = 64, 720000

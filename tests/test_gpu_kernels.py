@@ -361,7 +361,11 @@ def test_rvq_bit_exact_vs_reference(lib, rvq_engine, golden_dir):
     # get_indices_from_code (RVQ:258-357)
     _, idx2 = eng.rvq_encode(x_in.cuda().contiguous(), lens.cuda(), want_quantized=False)
     r2 = torch.from_numpy(z["indices_from_code"])
-    assert (idx2.cpu() == r2).float().mean() > 0.995
+    idx2 = idx2.cpu()
+    assert torch.equal(idx2 < 0, r2 < 0)
+    for b, t in (idx2 != r2).any(-1).nonzero().tolist():          # exact, or an fp64-verified tie at the first divergence
+        ql = int((idx2[b, t] != r2[b, t]).nonzero()[0])
+        assert _near_tie(W, x_in[b, t], r2[b, t], idx2[b, t], ql), (b, t, idx2[b, t], r2[b, t])
 
 
 def test_rvq_random_vs_oracle(lib, rvq_engine):
