@@ -126,20 +126,25 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port on the host cores (one utterance of the same workload per step)
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_step_factory(tokens: int, layers: int):
+def cpu_step_factory(tokens: int, layers: int, rows=None):
+    """One utterance per step through the CPU oracle.  `rows`: optional list of (wav [N] f32, ids [T], word ids [T]) host
+    tensors — utterances of the batch the GPU arm timed, so the oracle's indices double as the bench's parity check."""
     from taste_spokenlm_b200 import synth
     from oracle import taste_oracle as O                       # checker / CPU baseline only
     torch.set_num_threads(os.cpu_count() or 1)
     cfg = synth.FULL if layers == synth.FULL.enc_layers else synth.TowerConfig(enc_layers=layers)
     W = synth.random_weights(cfg, 1234)
-    b = synth.synth_batch(11, [UTT_SECONDS], [tokens])
+    if rows is None:
+        b = synth.synth_batch(11, [UTT_SECONDS], [tokens])
+        rows = [(b["wav"][0], b["asr_token_ids"][0], b["asr_word_ids"][0])]
 
-    def step():
+    def step(i: int = 0):
+        wav, ids, wid = rows[i % len(rows)]
         with torch.no_grad():
-            feats, _ = O.log_mel(b["wav"])
-            out = O.tower_forward(W, b["asr_token_ids"], b["asr_token_lengths"], feats, b["asr_word_ids"], cfg.heads,
-                                  cfg.enc_layers, cfg.dec_layers, cfg.num_quantizers, cfg.target_hidden_layer)
-        return out["quantized_indices"]
+            feats, _ = O.log_mel(wav[None])
+            out = O.tower_forward(W, ids[None], torch.tensor([ids.shape[0]], dtype=torch.int32), feats, wid[None],
+                                  cfg.heads, cfg.enc_layers, cfg.dec_layers, cfg.num_quantizers, cfg.target_hidden_layer)
+        return out["quantized_indices"][0]
     return step
 
 
@@ -148,10 +153,10 @@ def run_reference_arm(args, rank):
         return
     step = cpu_step_factory(args.tokens, args.layers)
     for _ in range(args.warmup):
-        step()
+        step(0)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        step(0)
     dt = time.perf_counter() - t0
     v = args.steps * UTT_SECONDS / dt
     cores = os.cpu_count() or 1
@@ -175,6 +180,201 @@ def workload_config(args, world, cpu=False):
         "batch_per_gpu": 1 if cpu else args.batch, "tokens_per_utt": args.tokens, "parallelism": f"dp{world} by utterance",
         "l2": "working set (>= 1.9 GB of activations per step) exceeds the 126 MB L2; no explicit flush",
     }
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE config 5: the tokenizer's share of an audio-conditioned inference_completion prompt (MT:1664-1704)
+# ---------------------------------------------------------------------------------------------------------------
+def measure_config5(tower, fe, batch, dev, args):
+    """B = 1 latency of the tokenizer call as `inference_completion` makes it: host tensors in (PT:246-247 leaves the
+    processor's outputs on the CPU, scripts/generate_audio.py:186-190 moves them), the drop-in `WhisperFrontend.forward`
+    + the patched `TasteForCausalLM.extract_vq` (tower forward incl. its state-key check and the token-length sync,
+    llm-token mapping), llm indices back on the host.  Wall clock around each call, median of 30 after 5 warm-ups.
+
+    Beside it, the LM side of the same prompt measured in this run on the same GPU: the reference's spoken LM is a
+    Llama-3.2-1B (`text_config` of configs/model/taslm.json) driven by `TasteSpokenLM.generate` (MT:1111-1117,
+    1196-1199), which re-forwards the WHOLE growing `inputs_embeds` on every step with no KV cache.  It is timed here as
+    HF transformers' stock `LlamaModel` (random init of that geometry, bf16, sdpa) + lm_head on a prompt of L llm
+    tokens followed by `new_tokens` re-forwards of L + k tokens; bridge, sampler and speech decoder are not included, so
+    the LM figure is a lower bound and the tokenizer share an upper bound."""
+    from taste_spokenlm_b200 import tower as T
+
+    class Model:                                   # stands in for TasteForCausalLM: extract_vq touches .audio_tower only
+        extract_vq = T.extract_vq
+
+    m = Model()
+    m.audio_tower = tower
+    Tn = args.tokens
+    wav_h = batch["wav"][:1].cpu()
+    ns_h = torch.tensor([480000], dtype=torch.int32)
+    ids_h, wid_h = batch["ids"][:1].cpu(), batch["wid"][:1].cpu()
+    len_h = torch.tensor([Tn], dtype=torch.int32)
+    n_words = int(wid_h.max()) + 1
+    g = torch.Generator().manual_seed(5)
+    pieces = torch.randint(1, 3, (n_words,), generator=g)
+    lwid_h = torch.repeat_interleave(torch.arange(n_words, dtype=torch.int32), pieces)[None]
+    L = lwid_h.shape[1]
+    llen_h = torch.tensor([L], dtype=torch.int32)
+    lids_h = torch.randint(0, 128256, (1, L), generator=g)
+    flen_h = torch.tensor([3000], dtype=torch.int32)
+
+    def call():
+        feats, _ = fe(wav_h.to(dev, non_blocking=True), ns_h)                       # WhisperFrontend.forward (WF:87-113)
+        _, llm_idx = m.extract_vq(ids_h.to(dev), len_h.to(dev), wid_h.to(dev), lids_h.to(dev), llen_h.to(dev),
+                                  lwid_h.to(dev), feats, flen_h.to(dev))            # MT:1695-1704
+        return llm_idx.cpu()
+
+    for _ in range(5):
+        out = call()
+    ts = []
+    for _ in range(30):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = call()
+        ts.append((time.perf_counter() - t0) * 1e3)
+    tok_ms = statistics.median(ts)
+    res = {"tokenizer_b1_e2e_ms": tok_ms, "tokenizer_b1_e2e_ms_min": min(ts), "asr_tokens": Tn, "llm_tokens": int(L),
+           "api": "host tensors -> WhisperFrontendB200.forward -> patched TasteForCausalLM.extract_vq -> llm indices on host"}
+    try:
+        from transformers import LlamaConfig, LlamaForCausalLM
+        cfg = LlamaConfig(hidden_size=2048, intermediate_size=8192, num_hidden_layers=16, num_attention_heads=32,
+                          num_key_value_heads=8, head_dim=64, vocab_size=128256, rms_norm_eps=1e-5, rope_theta=500000.0,
+                          max_position_embeddings=131072, tie_word_embeddings=True)
+        with torch.device(dev):
+            lm = LlamaForCausalLM(cfg).to(torch.bfloat16).eval()
+        new_tokens = 48                                   # extra_words = 32 (MT:1670) at ~1.5 llm tokens per word
+        emb = torch.randn(1, L + new_tokens, 2048, device=dev, dtype=torch.bfloat16) * 0.02
+
+        def prefill():
+            return lm.lm_head(lm.model(inputs_embeds=emb[:, :L], use_cache=False).last_hidden_state)
+
+        def generate_like_reference():
+            for k in range(new_tokens):                   # MT:1111-1117: whole sequence re-forwarded every step
+                lm.lm_head(lm.model(inputs_embeds=emb[:, : L + k], use_cache=False).last_hidden_state)
+
+        def timed(fn, n):
+            fn()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) * 1e3 / n
+
+        pre_ms = timed(prefill, 5)
+        gen_ms = timed(generate_like_reference, 2)
+        res.update({"lm_prefill_ms": pre_ms, "lm_generate_ms": gen_ms, "lm_new_tokens": new_tokens,
+                    "lm": "HF transformers LlamaForCausalLM, random-init Llama-3.2-1B geometry (taslm.json text_config), bf16, "
+                          "no KV cache as MT:1111-1117; measured in this run on the same GPU; bridge / sampler / speech "
+                          "decoder excluded",
+                    "tokenizer_share_of_prompt": tok_ms / (tok_ms + pre_ms),
+                    "tokenizer_share_of_completion": tok_ms / (tok_ms + gen_ms)})
+        del lm
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        res["lm_error"] = f"{type(e).__name__}: {str(e)[:200]}"
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE configs 3 / 4: ragged corpus through the real corpus driver (strong scaling)
+# ---------------------------------------------------------------------------------------------------------------
+def run_corpus(args, rank, world, local_rank):
+    import shutil
+    import tempfile
+    import torch.distributed as dist
+    from taste_spokenlm_b200 import _lib, shard, synth
+    from taste_spokenlm_b200.tower import TasteAudioTowerB200
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    cfg = synth.FULL if args.layers == synth.FULL.enc_layers else synth.TowerConfig(enc_layers=args.layers)
+    torch.set_grad_enabled(False)
+    tower = TasteAudioTowerB200.from_config(cfg).eval()
+    tower.load_state_dict(synth.random_weights(cfg, 1234), strict=True)
+    tower = tower.to(dev)
+    eng = tower.engine()
+    corpus = synth.SynthCorpus(args.utts, seed=4, pool=args.pool)
+    out_dir = tempfile.mkdtemp(prefix=f"taste_corpus_r{rank}_")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up: a small corpus of the same distribution through the same driver (allocations, first-launch costs)
+    warm = synth.SynthCorpus(args.batch * 3 * world, seed=5, pool=2)
+    shard.tokenize_corpus(eng, warm, world, rank, batch_size=args.batch, writer=shard.ShardWriter(out_dir + "/warm", rank),
+                          gather=True)
+    barrier()
+    launches0 = lib.taste_launch_count()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    tm = {}
+    writer = shard.ShardWriter(out_dir, rank, flush_every=2048)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    got = shard.tokenize_corpus(eng, corpus, world, rank, batch_size=args.batch, writer=writer, gather=True, timings=tm)
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    t_fin0 = time.perf_counter()
+    writer.finalize()
+    fin_ms = (time.perf_counter() - t_fin0) * 1e3
+    launches = int(lib.taste_launch_count() - launches0)
+    my_ms = e0.elapsed_time(e1)
+    all_ms = torch.tensor([my_ms], device=dev)
+    stats = torch.tensor([tm["fetch_ms"], tm["stall_ms"], tm["result_wait_ms"], tm["writer_ms"], tm["gather_ms"],
+                          float(tm["batches"]), float(tm["h2d_bytes"]), float(tm["d2h_bytes"])], device=dev, dtype=torch.float64)
+    if world > 1:
+        gl = [torch.zeros_like(all_ms) for _ in range(world)]
+        dist.all_gather(gl, all_ms)
+        rank_ms = [float(t.item()) for t in gl]
+        sl = [torch.zeros_like(stats) for _ in range(world)]
+        dist.all_gather(sl, stats)
+        stats_all = torch.stack(sl).cpu()
+    else:
+        rank_ms = [my_ms]
+        stats_all = stats[None].cpu()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    ok = len(got) == args.utts and all(int(t.shape[0]) == corpus.token_counts[u] for u, t in got[:: max(1, args.utts // 256)])
+    shutil.rmtree(out_dir, ignore_errors=True)
+    if rank == 0:
+        ms = max(rank_ms)
+        nb = stats_all[:, 5]
+        per_batch = lambda col: float((stats_all[:, col] / nb.clamp_min(1)).max())      # noqa: E731
+        line = {
+            "metric": "audio-sec tokenized/sec (ragged 1-30 s corpus)", "value": corpus.audio_seconds / (ms / 1e3), "unit": UNIT,
+            "windows_audio_s_per_s": args.utts * UTT_SECONDS / (ms / 1e3), "utt_per_s": args.utts / (ms / 1e3),
+            "n_gpus": world, "steps": int(nb.max()), "warmup": 3, "ms_per_step": ms / max(float(nb.max()), 1.0),
+            "ms_total": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"configs[2]/[3]: {args.utts} utterances, durations U[1,30] s (mean {corpus.audio_seconds / args.utts:.1f} s), "
+                                   f"T = clip(round(2.7 dur + N(0,2)), 1, 443) (mean {np.mean(corpus.token_counts):.1f}), seed 4; "
+                                   f"length-bucketed batches of {args.batch}; host-resident audio, double-buffered pinned H2D, "
+                                   f"tokenize + llm-token mapping, ShardWriter (Arrow, load_from_disk layout), final all-gather",
+                       "geometry": f"distil-large-v3 tower: d_model 1280, {args.layers} encoder layers, random init",
+                       "parallelism": f"dp{world} by utterance (shard_indices round-robin inside length buckets)",
+                       "note": "every utterance costs one full 30 s encoder window (SURVEY 0.3): windows/s is the rate the GPU "
+                               "sees, real audio-s/s the rate the corpus sees"},
+            "rank_ms": {"max": max(rank_ms), "min": min(rank_ms)},
+            "host_ms_per_batch_max_over_ranks": {"fetch (worker thread, overlapped)": per_batch(0), "stall (compute thread waits for worker)": per_batch(1),
+                                                  "result_wait": per_batch(2), "writer": per_batch(3)},
+            "gather_ms": float(stats_all[:, 4].max()), "writer_ms_total": float(stats_all[:, 3].max()), "finalize_ms": fin_ms,
+            "e2e": {"value": corpus.audio_seconds / (ms / 1e3), "unit": UNIT,
+                    "h2d_bytes_per_step": float((stats_all[:, 6] / nb.clamp_min(1)).mean()),
+                    "d2h_bytes_per_step": float((stats_all[:, 7] / nb.clamp_min(1)).mean()),
+                    "api": "shard.tokenize_corpus (host corpus in, Arrow shards + gathered indices out)"},
+            "gpu_launches": launches, "clocks": clocks, "complete": bool(ok),
+        }
+        if args.layers != 32:
+            line["INVALID"] = "debug run with a reduced layer count; not the named config"
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -211,6 +411,11 @@ def main():
     ap.add_argument("--layers", type=int, default=32, help="encoder layers (32 = the named config; others are for debugging and flagged)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-config5", action="store_true")
+    ap.add_argument("--workload", default="fixed", choices=["fixed", "corpus"],
+                    help="fixed = configs[1] (the headline); corpus = configs[2]/[3] through shard.tokenize_corpus (strong scaling)")
+    ap.add_argument("--utts", type=int, default=16384, help="corpus workload: utterances in the whole job")
+    ap.add_argument("--pool", type=int, default=64, help="corpus workload: distinct decoded waveforms held on the host")
     ap.add_argument("--encoder-mode", type=int, default=0, help="taste_encoder_set_mode (A/B runs): 0 default, 1 no LayerNorm folding, 2 fold both")
     args = ap.parse_args()
 
@@ -220,6 +425,11 @@ def main():
 
     if args.impl == "reference":
         run_reference_arm(args, rank)
+        return
+    if args.workload == "corpus":
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+        run_corpus(args, rank, world, local_rank)
         return
 
     import torch.distributed as dist
@@ -369,6 +579,10 @@ def main():
         torch.cuda.synchronize()
         lat_ms = g0.elapsed_time(g1) / 10
 
+    config5 = None
+    if rank == 0 and not args.no_e2e and not args.no_config5:
+        config5 = measure_config5(tower, fe, batch, dev, args)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -379,7 +593,7 @@ def main():
     stages = []
     tot_kernel_ms = sum(p["total_ms"] for p in prof) or 1.0
     for p in sorted(prof, key=lambda r: -r["total_ms"]):
-        tensor = p["name"].startswith("gemm") or p["name"].startswith("attention")
+        tensor = p["name"].startswith("gemm") or p["name"].startswith("attention") or p["name"].startswith("rvq_encode")
         sec = p["total_ms"] / 1e3
         if tensor:
             ach, peak, unit = p["flops"] / sec / 1e12, peaks["bf16_tflops_sustained"], "TFLOP/s"
@@ -401,24 +615,36 @@ def main():
     if top:
         roofline = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"],
                     "unit": top["unit"], "frac": top["frac"], "traffic": traffic,
+                    "traffic_source": "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch from the "
+                                      "committed ncu --set full capture (scripts/gpu_ncu.sh), not re-measured in this run",
                     "peak_source": f"MEASURED_PEAKS.json ({peaks['source']}), sustained bf16 (kernel timed inside a long step)"
                     if top["bound"] == "tensor" else f"MEASURED_PEAKS.json ({peaks['source']}) hbm_gbs",
                     "avg_launch_ms": top["ms_per_step"] / max(top["launches_per_step"], 1e-9)}
     flops_per_utt = sum(p["flops"] for p in prof) / (args.steps * B)
 
     cpu_baseline = None
+    parity_check = None
     if world == 1 and not args.no_cpu_baseline:
-        step = cpu_step_factory(args.tokens, args.layers)
-        step()
-        reps = 2
+        # the CPU leg runs utterances 0 .. reps of the batch that was just timed: its indices are the parity check of
+        # the timed output (the timed batch itself was never compared with the oracle)
+        reps = 3
+        rows = [(batch["wav"][i].cpu(), batch["ids"][i].cpu(), batch["wid"][i].cpu()) for i in range(reps)]
+        step = cpu_step_factory(args.tokens, args.layers, rows)
+        ref_rows = [step(0)]                                   # warm-up, kept as a checked row
         t0 = time.perf_counter()
-        for _ in range(reps):
-            ref_idx = step()
-        dt = (time.perf_counter() - t0) / reps
+        for i in range(1, reps):
+            ref_rows.append(step(i))
+        dt = (time.perf_counter() - t0) / (reps - 1)
         cores = os.cpu_count() or 1
         cpu_baseline = {"value": UTT_SECONDS / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"{reps} x 1 utterance (30 s, {args.tokens} tokens) of the batch-64 workload after 1 warm-up, "
+                        "sample": f"{reps - 1} x 1 utterance (30 s, {args.tokens} tokens) of the timed batch after 1 warm-up, "
                                   f"fp32 oracle (torch CPU, {cores} threads), {dt:.2f} s per utterance"}
+        got = idx[:reps].cpu()
+        ref = torch.stack(ref_rows)
+        lvl = [float((got[..., q] == ref[..., q]).float().mean()) for q in range(ref.shape[-1])]
+        parity_check = {"utterances": reps, "n_indices": int(ref.numel()), "index_agreement": float((got == ref).float().mean()),
+                        "per_level": lvl, "against": "fp32 CPU oracle on utterances 0..2 of the timed batch (device-resident arm; "
+                                                     "the e2e arm is asserted bit-equal to it)"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -427,8 +653,8 @@ def main():
         "utt_per_s": value / UTT_SECONDS, "per_gpu": value / world,
         "tflops_per_gpu": flops_per_utt * (value / UTT_SECONDS / world) / 1e12,
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "stages": stages,
-        "cpu_baseline": cpu_baseline,
-        "latency_b1_ms": lat_ms,
+        "cpu_baseline": cpu_baseline, "parity_check": parity_check,
+        "latency_b1_ms": lat_ms, "config5": config5,
     }
     if args.layers != 32:
         line["INVALID"] = "debug run with a reduced layer count; not the named config"

@@ -308,3 +308,91 @@ def synth_pcm(seed: int, n: int, channels: int = 1):
         x += 0.1 * torch.sin(2 * 3.141592653589793 * f * t + ph)[None] * torch.rand(channels, 1, generator=g, dtype=torch.float64)
     x = x.to(torch.float32).numpy()
     return x[0] if channels == 1 else np.ascontiguousarray(x)
+
+
+class SynthCorpus:
+    """BASELINE configs 3 / 4: a host-resident corpus of ragged utterances (no dataset exists offline).
+
+    Durations ~ U[1, 30] s; transcript length T = clip(round(2.7 * duration + N(0, 2)), 1, 443); word ids
+    as in `synth_transcript`; an llm tokenisation of the same words with 1-3 sub-word tokens per word (the columns the
+    reference's extract_vq job writes, XV:51-58).  Decoded audio lives in ordinary host memory as the data loader would
+    leave it: `pool` distinct 30 s waveforms, utterance u plays `pool[u % pool][:n_samples[u]]` (holding 16 384 distinct
+    waveforms would take 31 GB and change nothing the path can see).  Implements both corpus protocols of
+    `shard.tokenize_corpus`: `fetch_host(indices, slot)` (pinned staging, the corpus job) and `load(indices)` (device).
+    """
+
+    wav_stride = 480000
+
+    def __init__(self, n_utts: int, seed: int = 4, pool: int = 64, max_tokens: int = 443):
+        import numpy as np
+        rng = np.random.default_rng(seed)
+        self.n = int(n_utts)
+        self.durations = rng.uniform(1.0, 30.0, self.n)
+        tc = np.clip(np.round(2.7 * self.durations + rng.normal(0.0, 2.0, self.n)), 1, max_tokens).astype(np.int64)
+        self.token_counts = tc.tolist()
+        self.n_samples = np.minimum((self.durations * 16000).astype(np.int64), self.wav_stride)
+        self.pool = np.stack([synth_waveform(seed * 7919 + p, self.wav_stride).numpy() for p in range(int(pool))])
+        self.off = np.zeros(self.n + 1, dtype=np.int64)
+        np.cumsum(tc, out=self.off[1:])
+        total = int(self.off[-1])
+        self.ids = rng.integers(0, 50257, total, dtype=np.int64)
+        starts = (rng.random(total) < 0.55)
+        starts[self.off[:-1]] = False
+        c = np.cumsum(starts)
+        self.wid = (c - np.repeat(c[self.off[:-1]], tc)).astype(np.int32)            # word id of every asr token
+        n_words = self.wid[self.off[1:] - 1].astype(np.int64) + 1
+        self.word_off = np.zeros(self.n + 1, dtype=np.int64)
+        np.cumsum(n_words, out=self.word_off[1:])
+        pieces = rng.integers(1, 4, int(self.word_off[-1]))
+        local_word = np.arange(int(self.word_off[-1])) - np.repeat(self.word_off[:-1], n_words)
+        self.llm_wid = np.repeat(local_word, pieces).astype(np.int32)
+        lcount = np.add.reduceat(pieces, self.word_off[:-1])
+        self.llm_off = np.zeros(self.n + 1, dtype=np.int64)
+        np.cumsum(lcount, out=self.llm_off[1:])
+        self.llm_ids = rng.integers(0, 128256, int(self.llm_off[-1]), dtype=np.int64)
+        self.llm_counts = lcount
+        self.max_llm_tokens = int(lcount.max())
+        self.audio_seconds = float(self.n_samples.sum() / 16000.0)
+
+    def fetch_host(self, indices, slot):
+        import numpy as np
+        idx = np.asarray(indices, dtype=np.int64)
+        B = len(idx)
+        tc = np.asarray([self.token_counts[i] for i in idx], dtype=np.int64)
+        T, L = int(tc.max()), int(self.llm_counts[idx].max())
+        wav, ids, wid, lwid = slot.wav_h.numpy(), slot.ids_h.numpy(), slot.wid_h.numpy(), slot.lwid_h.numpy()
+        ids[:B, :T] = 0
+        wid[:B, :T] = 0
+        lwid[:B, :L] = 0
+        llm_ids = np.zeros((B, L), dtype=np.int64)
+        for r, u in enumerate(idx):
+            n = int(self.n_samples[u])
+            wav[r, :n] = self.pool[u % len(self.pool), :n]
+            a0, a1 = self.off[u], self.off[u + 1]
+            ids[r, : a1 - a0] = self.ids[a0:a1]
+            wid[r, : a1 - a0] = self.wid[a0:a1]
+            l0, l1 = self.llm_off[u], self.llm_off[u + 1]
+            lwid[r, : l1 - l0] = self.llm_wid[l0:l1]
+            llm_ids[r, : l1 - l0] = self.llm_ids[l0:l1]
+        slot.ns_h.numpy()[:B] = self.n_samples[idx]
+        slot.len_h.numpy()[0, :B] = tc
+        slot.len_h.numpy()[1, :B] = self.llm_counts[idx]
+        return {"B": B, "T": T, "L": L, "lengths_host": tc, "llm_lengths_host": self.llm_counts[idx].copy(),
+                "max_n": int(self.n_samples[idx].max()), "llm_ids": llm_ids}
+
+    def load(self, indices, device="cuda"):
+        """Device-resident protocol (small jobs / tests): the same rows as tensors on `device`."""
+        import numpy as np
+        idx = np.asarray(indices, dtype=np.int64)
+        tc = np.asarray([self.token_counts[i] for i in idx], dtype=np.int64)
+        T = int(tc.max())
+        wav = torch.zeros(len(idx), self.wav_stride)
+        ids = torch.zeros(len(idx), T, dtype=torch.int64)
+        wid = torch.zeros(len(idx), T, dtype=torch.int32)
+        for r, u in enumerate(idx):
+            n = int(self.n_samples[u])
+            wav[r, :n] = torch.from_numpy(self.pool[u % len(self.pool), :n])
+            ids[r, : tc[r]] = torch.from_numpy(self.ids[self.off[u]: self.off[u + 1]])
+            wid[r, : tc[r]] = torch.from_numpy(self.wid[self.off[u]: self.off[u + 1]])
+        return {"wav": wav.to(device), "n_samples": torch.from_numpy(self.n_samples[idx].astype(np.int32)).to(device),
+                "ids": ids.to(device), "wid": wid.to(device), "lengths_host": tc}

@@ -100,20 +100,52 @@ def test_shard_writer_streams_and_resumes(tmp_path):
         li = rng.integers(-1, 512, (L, 4))
         ref[u] = li
         w.add(u, li, rng.integers(0, 32000, L), np.arange(L))
-    assert len(w.manifest["files"]) == 2 and sorted(w.manifest["done"]) == [0, 1, 2, 3, 4, 5]      # 7th still buffered
+    assert len(w.manifest["files"]) == 2 and sorted(w.done_ids()) == [0, 1, 2, 3, 4, 5]      # 7th still buffered
     # a crash here loses only the unflushed utterance; a restarted rank skips the six on disk
     w2 = shard.ShardWriter(str(tmp_path), rank=1, flush_every=3)
     assert w2.pending(range(9)).tolist() == [6, 7, 8]
     assert w2.is_done(5) and not w2.is_done(6)
-    for u in (6, 7, 8):
-        L = 4
-        li = rng.integers(-1, 512, (L, 4))
-        ref[u] = li
-        w2.add(u, li, rng.integers(0, 32000, L), np.arange(L))
+    # the batched entry point: padded arrays + lengths
+    lens = [4, 2, 5]
+    li = rng.integers(-1, 512, (3, 5, 4))
+    for r, u in enumerate((6, 7, 8)):
+        ref[u] = li[r, : lens[r]]
+    w2.add_batch([6, 7, 8], li, rng.integers(0, 32000, (3, 5)), np.tile(np.arange(5), (3, 1)), lens)
     w2.close()
     rows = w2.read_all()
     assert [r["utt_id"] for r in rows] == list(range(9))
     for r in rows:
         assert set(r) == set(shard.ShardWriter.COLUMNS)
-        assert np.array_equal(np.asarray(r["llm_indices"]), ref[r["utt_id"]])
-        assert r["llm_token_lengths"] == len(r["llm_token_ids"]) == len(r["llm_word_ids"])
+        # the reference's row shapes (XV:51-58): [1, L, Q], [1, L], [1], [1, L]
+        assert np.array_equal(np.asarray(r["llm_indices"])[0], ref[r["utt_id"]]) and len(r["llm_indices"]) == 1
+        assert r["llm_token_lengths"] == [len(r["llm_token_ids"][0])] == [len(r["llm_word_ids"][0])]
+
+
+def test_shard_writer_output_opens_with_datasets_load_from_disk(tmp_path):
+    """Stage-2 training reads the parts with `datasets.load_from_disk` (scripts/run.py:347); the reference writes them
+    with `Dataset.from_list(results).save_to_disk` (XV:161-162).  Same rows through both paths must read back equal."""
+    datasets = pytest.importorskip("datasets")
+    rng = np.random.default_rng(1)
+    w = shard.ShardWriter(str(tmp_path / "ours"), rank=0, flush_every=4)
+    results = []
+    for u in range(10):
+        L = int(rng.integers(1, 12))
+        li = rng.integers(-1, 512, (L, 4))
+        ids, wid = rng.integers(0, 128256, L), np.sort(rng.integers(0, L, L))
+        w.add(u, li, ids, wid)
+        results.append({                                              # what ExtractVQTrainer.prediction_step appends
+            "llm_indices": torch.from_numpy(li)[None].to(torch.int64),
+            "llm_token_ids": torch.from_numpy(ids)[None].to(torch.int64),
+            "llm_token_lengths": torch.tensor([L], dtype=torch.int32),
+            "llm_word_ids": torch.from_numpy(wid)[None].to(torch.int32),
+        })
+    path = w.finalize()
+    ours = datasets.load_from_disk(path)
+    ref_dir = str(tmp_path / "ref")
+    datasets.Dataset.from_list(results).save_to_disk(ref_dir)
+    ref = datasets.load_from_disk(ref_dir)
+    assert len(ours) == len(ref) == 10
+    for col in ("llm_indices", "llm_token_ids", "llm_token_lengths", "llm_word_ids"):
+        assert ours[col] == ref[col] if not hasattr(ours[col], "to_pylist") else list(ours[col]) == list(ref[col]), col
+        assert ours.features[col] == ref.features[col], (col, ours.features[col], ref.features[col])
+    assert list(ours["utt_id"]) == list(range(10))
