@@ -412,6 +412,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-config5", action="store_true")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"],
+                    help="library flavour of the headline arm (bf16 = BASELINE config 2's dtype)")
+    ap.add_argument("--no-alt-precision", action="store_true", help="skip the second, other-flavour timing of the same step")
     ap.add_argument("--workload", default="fixed", choices=["fixed", "corpus"],
                     help="fixed = configs[1] (the headline); corpus = configs[2]/[3] through shard.tokenize_corpus (strong scaling)")
     ap.add_argument("--utts", type=int, default=16384, help="corpus workload: utterances in the whole job")
@@ -445,15 +448,16 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    lib = _lib.load()
-    _lib.check(lib.taste_encoder_set_mode(args.encoder_mode), "taste_encoder_set_mode")
+    lib = _lib.load(args.precision)
+    _lib.check(lib.taste_encoder_set_mode(args.encoder_mode), "taste_encoder_set_mode", lib)
 
     cfg = synth.FULL if args.layers == synth.FULL.enc_layers else synth.TowerConfig(enc_layers=args.layers)
     torch.set_grad_enabled(False)
-    tower = TasteAudioTowerB200.from_config(cfg).eval()
-    tower.load_state_dict(synth.random_weights(cfg, 1234), strict=True)
+    weights = synth.random_weights(cfg, 1234)
+    tower = TasteAudioTowerB200.from_config(cfg, precision=args.precision).eval()
+    tower.load_state_dict(weights, strict=True)
     tower = tower.to(dev)
-    fe = WhisperFrontendB200(whisper_model="large-v3", do_pad_trim=True, permute=True).to(dev)
+    fe = WhisperFrontendB200(whisper_model="large-v3", do_pad_trim=True, permute=True, precision=args.precision).to(dev)
     eng = tower.engine()
 
     batch = make_batch(1000 + rank, args.batch, args.tokens, dev)
@@ -498,8 +502,40 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-    prof = _lib.prof_collect()
+    prof = _lib.prof_collect(lib)
     lib.taste_prof_reset()
+
+    # ---- the same step in the other library flavour (same kernels, other 16-bit operand type) ----------------------
+    alt = None
+    if not args.no_alt_precision:
+        other = "fp16" if args.precision == "bf16" else "bf16"
+        tower2 = TasteAudioTowerB200.from_config(cfg, precision=other).eval()
+        tower2.load_state_dict(weights, strict=True)
+        tower2 = tower2.to(dev)
+        eng2 = tower2.engine()
+
+        def step2():
+            return eng2.tokenize_device(batch["wav"], batch["n_samples"], batch["ids"], batch["wid"], batch["lengths_host"])
+
+        for _ in range(max(args.warmup, 3)):
+            _, idx2 = step2()
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(args.steps):
+            _, idx2 = step2()
+        a1.record()
+        barrier()
+        ms_alt = torch.tensor([a0.elapsed_time(a1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms_alt, op=dist.ReduceOp.MAX)
+        alt = {"dtype": other, "value": world * B * UTT_SECONDS * args.steps / (float(ms_alt.item()) / 1e3), "unit": UNIT,
+               "ms_per_step": float(ms_alt.item()) / args.steps,
+               "index_agreement_with_headline_arm": float((idx2 == idx).float().mean()),
+               "note": "same workload and step, library flavour with the other 16-bit operand type "
+                       "(libtaste_b200_f16.so = fp16 operands: the reference's own autocast dtype, JES:133)"}
+        del tower2, eng2
+        torch.cuda.empty_cache()
 
     # ---- end-to-end timing through the drop-in modules with host buffers ----------------------------------------
     e2e = None
@@ -649,11 +685,11 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world),
+        "dtype": args.precision, "data": "synthetic", "config": workload_config(args, world),
         "utt_per_s": value / UTT_SECONDS, "per_gpu": value / world,
         "tflops_per_gpu": flops_per_utt * (value / UTT_SECONDS / world) / 1e12,
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "stages": stages,
-        "cpu_baseline": cpu_baseline, "parity_check": parity_check,
+        "cpu_baseline": cpu_baseline, "parity_check": parity_check, "alt_precision": alt,
         "latency_b1_ms": lat_ms, "config5": config5,
     }
     if args.layers != 32:

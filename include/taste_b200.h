@@ -29,7 +29,13 @@
 extern "C" {
 #endif
 
-#define TASTE_ABI_VERSION 3
+#define TASTE_ABI_VERSION 4
+
+/* Library flavour: the 16-bit type of every tensor-core operand buffer below that is documented as "bf16" (packed
+ * weights, log-mel features for the stem, encoder states h_last / h_target, GEMM / attention operands).
+ * 0 = bf16 (libtaste_b200.so; BASELINE config 2), 1 = fp16 (libtaste_b200_f16.so, built with -DTASTE_F16=1: the
+ * reference's own GPU dtype under torch.cuda.amp.autocast(), JES:133 / JES:336).  fp32 buffers are fp32 in both. */
+int taste_operand_dtype(void);
 
 #define TASTE_E_ARG        (-1)  /* null pointer / bad size */
 #define TASTE_E_SHAPE      (-2)  /* geometry not supported by the kernels (see taste_handle_create) */

@@ -8,6 +8,10 @@ import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtaste_b200.so")
+# Library flavours (csrc/common.cuh, TASTE_F16): the 16-bit type of every tensor-core operand.  bf16 is BASELINE config 2's
+# dtype and the default; fp16 is the reference's own GPU dtype (autocast, JES:133) with 3 more mantissa bits at the same
+# tensor-core rate.  Select with `precision=` on the modules / engines or TASTE_PRECISION in the environment.
+LIB_PATHS = {"bf16": LIB_PATH, "fp16": os.path.join(_HERE, "libtaste_b200_f16.so")}
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "taste_b200.h")
 
 DFT_LD = 224
@@ -64,6 +68,7 @@ _SIGS = {
     "taste_prof_reset": (C.c_int, []),
     "taste_prof_collect": (C.c_int, [C.POINTER(ProfEntry), C.c_int, C.POINTER(C.c_int)]),
     "taste_abi_version": (C.c_int, []),
+    "taste_operand_dtype": (C.c_int, []),
     "taste_last_error": (C.c_char_p, []),
     "taste_handle_create": (C.c_int, [C.POINTER(Weights), C.POINTER(p)]),
     "taste_handle_destroy": (C.c_int, [p]),
@@ -89,7 +94,20 @@ _SIGS = {
                                        C.c_int, C.c_int, C.c_int, p]),
 }
 
-_lib = None
+_libs = {}
+
+
+def resolve_precision(precision=None) -> str:
+    p = (precision or os.environ.get("TASTE_PRECISION") or "bf16").lower()
+    p = {"bfloat16": "bf16", "float16": "fp16", "f16": "fp16", "half": "fp16"}.get(p, p)
+    if p not in LIB_PATHS:
+        raise TasteError(f"unknown precision {precision!r}: expected 'bf16' or 'fp16'")
+    return p
+
+
+def torch_dtype(precision=None):
+    import torch
+    return torch.float16 if resolve_precision(precision) == "fp16" else torch.bfloat16
 
 
 class TasteError(RuntimeError):
@@ -103,36 +121,41 @@ def declared_symbols(header_path: str = HEADER_PATH):
     return sorted(set(re.findall(r"\b(taste_[a-z0-9_]+)\s*\(", txt)))
 
 
-def load():
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
-        raise TasteError(f"{LIB_PATH} not found: run `python __graft_entry__.py` (build()) first; there is no CPU fallback")
-    lib = C.CDLL(LIB_PATH)
+def load(precision=None):
+    """dlopen the library of the given flavour (default: TASTE_PRECISION or bf16) and bind every declared symbol."""
+    precision = resolve_precision(precision)
+    if precision in _libs:
+        return _libs[precision]
+    path = LIB_PATHS[precision]
+    if not os.path.exists(path):
+        raise TasteError(f"{path} not found: run `python __graft_entry__.py` (build()) first; there is no CPU fallback")
+    lib = C.CDLL(path)
     for name, (res, args) in _SIGS.items():
         try:
             fn = getattr(lib, name)
         except AttributeError as e:
-            raise TasteError(f"libtaste_b200.so does not export {name}") from e
+            raise TasteError(f"{os.path.basename(path)} does not export {name}") from e
         fn.restype = res
         fn.argtypes = args
-    _lib = lib
+    if lib.taste_operand_dtype() != (1 if precision == "fp16" else 0):
+        raise TasteError(f"{os.path.basename(path)} was not built for {precision} operands")
+    lib.precision = precision
+    _libs[precision] = lib
     return lib
 
 
-def check(rc: int, what: str = ""):
+def check(rc: int, what: str = "", lib=None):
     if rc != 0:
-        msg = load().taste_last_error().decode(errors="replace")
+        msg = (lib or load()).taste_last_error().decode(errors="replace")
         raise TasteError(f"{what} failed (code {rc}): {msg}")
 
 
-def prof_collect():
+def prof_collect(lib=None):
     """[{name, launches, total_ms, flops, bytes}] for every kernel class launched since the last taste_prof_reset()."""
-    lib = load()
+    lib = lib or load()
     arr = (ProfEntry * 32)()
     n = C.c_int(0)
-    check(lib.taste_prof_collect(arr, 32, C.byref(n)), "taste_prof_collect")
+    check(lib.taste_prof_collect(arr, 32, C.byref(n)), "taste_prof_collect", lib)
     return [dict(name=arr[i].name.decode(), launches=int(arr[i].launches), total_ms=float(arr[i].total_ms),
                  flops=float(arr[i].flops), bytes=float(arr[i].bytes)) for i in range(n.value)]
 

@@ -114,6 +114,8 @@ MelWs carve_logmel(int batch, void* ws) {
 
 extern "C" {
 
+int taste_operand_dtype(void) { return TASTE_F16 ? 1 : 0; }
+
 int taste_abi_version(void) { return TASTE_ABI_VERSION; }
 const char* taste_last_error(void) { return taste::g_err; }
 

@@ -45,7 +45,11 @@ TASTE_DEVINL void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint3
 }
 TASTE_DEVINL void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
+      #if TASTE_F16
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+#else
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+#endif
       "{%0, %1, %2, %3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -201,11 +205,11 @@ attention_mma_kernel(const AttnParams p) {
       rs[1] += p2 + p3;
       const int ks = i >> 1;
       if ((i & 1) == 0) {
-        pf[ks][0] = pack_bf16x2(p0, p1);
-        pf[ks][1] = pack_bf16x2(p2, p3);
+        pf[ks][0] = pack_act2(p0, p1);
+        pf[ks][1] = pack_act2(p2, p3);
       } else {
-        pf[ks][2] = pack_bf16x2(p0, p1);
-        pf[ks][3] = pack_bf16x2(p2, p3);
+        pf[ks][2] = pack_act2(p0, p1);
+        pf[ks][3] = pack_act2(p2, p3);
       }
     }
 #pragma unroll
@@ -249,11 +253,11 @@ attention_mma_kernel(const AttnParams p) {
     const int col = i * 8 + (lane & 3) * 2;
     if (r0 < q_rows) {
       *reinterpret_cast<uint32_t*>(go + int64_t(q_start + q0 + r0) * p.ldo + col) =
-          pack_bf16x2(o_acc[i][0] * inv0, o_acc[i][1] * inv0);
+          pack_act2(o_acc[i][0] * inv0, o_acc[i][1] * inv0);
     }
     if (r0 + 8 < q_rows) {
       *reinterpret_cast<uint32_t*>(go + int64_t(q_start + q0 + r0 + 8) * p.ldo + col) =
-          pack_bf16x2(o_acc[i][2] * inv1, o_acc[i][3] * inv1);
+          pack_act2(o_acc[i][2] * inv1, o_acc[i][3] * inv1);
     }
   }
 }

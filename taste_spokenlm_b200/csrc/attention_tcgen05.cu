@@ -233,8 +233,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
     // softmax warps can satisfy (with a single issuer and a fixed wait order the two warpgroups throttled each other).
     FA_REGS_SMALL();
     const int i = warp - kMmaWarp0;
-    constexpr uint32_t idesc_qk = umma_idesc(FA_BQ, FA_BK, 1, 0, 0);        // A, B K-major
-    constexpr uint32_t idesc_pv = umma_idesc(FA_BQ, FA_HD, 1, 0, 1);        // A from TMEM, B (V) MN-major
+    constexpr uint32_t idesc_qk = umma_idesc(FA_BQ, FA_BK, kActBf16, 0, 0);        // A, B K-major
+    constexpr uint32_t idesc_pv = umma_idesc(FA_BQ, FA_HD, kActBf16, 0, 1);        // A from TMEM, B (V) MN-major
     // No integer division in this loop: I2F / MUFU.RCP / F2I queue behind the softmax warps' exponentials on the XU
     // pipe (in-kernel timeline: 600-700 cycles per loop step, which left the issuers with no slack at all), so the
     // position of the block whose QK^T is issued next (one ahead of the block whose P V is issued) is carried along.
@@ -366,10 +366,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o[8 * e + 0]) * inv, __uint_as_float(o[8 * e + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(o[8 * e + 2]) * inv, __uint_as_float(o[8 * e + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(o[8 * e + 4]) * inv, __uint_as_float(o[8 * e + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(o[8 * e + 6]) * inv, __uint_as_float(o[8 * e + 7]) * inv);
+          u.x = pack_act2(__uint_as_float(o[8 * e + 0]) * inv, __uint_as_float(o[8 * e + 1]) * inv);
+          u.y = pack_act2(__uint_as_float(o[8 * e + 2]) * inv, __uint_as_float(o[8 * e + 3]) * inv);
+          u.z = pack_act2(__uint_as_float(o[8 * e + 4]) * inv, __uint_as_float(o[8 * e + 5]) * inv);
+          u.w = pack_act2(__uint_as_float(o[8 * e + 6]) * inv, __uint_as_float(o[8 * e + 7]) * inv);
           srow[(hc * 4 + e) ^ (lane & 7)] = u;
         }
       }
@@ -524,7 +524,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
                 }
               }
               sum2 = f2_add(sum2, f2_pack(p0, p1));
-              pk[e] = pack_bf16x2(p0, p1);
+              pk[e] = pack_act2(p0, p1);
             }
             if (kTurn && c == 0 && j > 0) {
               // Only now is the previous block's P V needed: P_i has been consumed (it may be overwritten) and O_i is
@@ -613,7 +613,7 @@ static int make_map(EncodeTiledFn enc, CUtensorMap* m, const void* base, int hea
   cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)rows};
   cuuint32_t box[3] = {FA_HD, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(m, kActBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error((int)r, "attention: tensor map encode failed (%d)", (int)r);

@@ -2,6 +2,17 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+// Library flavour (compile time): the 16-bit type of every tensor-core operand the path produces and consumes
+// (activations, packed weights, softmax probabilities).  0 = bf16 (libtaste_b200.so, BASELINE config 2's dtype),
+// 1 = fp16 (libtaste_b200_f16.so: the reference's own GPU dtype - `torch.cuda.amp.autocast()` defaults to fp16, JES:133,
+// JES:336 - with 3 more mantissa bits at the same tensor-core rate).  Accumulators, the residual stream, LayerNorm
+// statistics, softmax state, the aggregator output and the RVQ are fp32 in both.  The log-mel DFT always runs on split
+// bf16 planes (see logmel.cu), whichever flavour.
+#ifndef TASTE_F16
+#define TASTE_F16 0
+#endif
 #include <cuda.h>
 #include <stdint.h>
 
@@ -256,6 +267,7 @@ TASTE_DEVINL uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes)
   return d;
 }
 // Instruction descriptor, kind::f16: D=f32, A/B = bf16 (1) or f16 (0).  a_mn/b_mn: 1 = MN-major operand.
+constexpr int kActBf16 = TASTE_F16 ? 0 : 1;
 __host__ __device__ constexpr uint32_t umma_idesc(int m, int n, int ab_fmt_bf16, int a_mn, int b_mn) {
   return (1u << 4) | (static_cast<uint32_t>(ab_fmt_bf16) << 7) | (static_cast<uint32_t>(ab_fmt_bf16) << 10) |
          (static_cast<uint32_t>(a_mn) << 15) | (static_cast<uint32_t>(b_mn) << 16) |
@@ -437,9 +449,18 @@ TASTE_DEVINL void exp2_poly2_sat(float s0, float s1, float c1, float c0, float& 
   p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(u1) << 23));
 }
 
-TASTE_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
+TASTE_DEVINL uint32_t pack_true_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+// Two fp32 values -> one packed pair of the library flavour's 16-bit operand type (see kActBf16).
+TASTE_DEVINL uint32_t pack_act2(float lo, float hi) {
+#if TASTE_F16
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+#else
+  return pack_true_bf16x2(lo, hi);
+#endif
 }
 
 TASTE_DEVINL float warp_sum(float v) {

@@ -54,8 +54,8 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
       o.w = (v[i].w - mean) * rstd * g.w + be.w;
       if (OUT_BF16) {
         uint2 u;
-        u.x = pack_bf16x2(o.x, o.y);
-        u.y = pack_bf16x2(o.z, o.w);
+        u.x = pack_act2(o.x, o.y);
+        u.y = pack_act2(o.z, o.w);
         reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(y) + int64_t(warp) * d)[idx] = u;
       } else {
         reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + int64_t(warp) * d)[idx] = o;
@@ -97,8 +97,8 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float4* __restrict
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 v = x[i];
     uint2 u;
-    u.x = pack_bf16x2(v.x, v.y);
-    u.y = pack_bf16x2(v.z, v.w);
+    u.x = pack_act2(v.x, v.y);
+    u.y = pack_act2(v.z, v.w);
     y[i] = u;
   }
 }

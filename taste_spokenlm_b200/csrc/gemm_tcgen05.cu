@@ -44,6 +44,7 @@ struct GemmParams {
   const float* ln_colsum;     // [n]
   float* stats_out;           // [rows][n / 128][2]
   __nv_bfloat16* out_bf16;    // [rows, ldc]
+  int ab_bf16;                // tcgen05 operand format: 1 = bf16, 0 = fp16
   int kclass;                 // host-side accounting only
   double alg_bytes;
 };
@@ -84,10 +85,10 @@ TASTE_DEVINL void epilogue_chunk(const uint32_t (&acc)[32], const GemmParams& p,
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       uint4 u;
-      u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-      u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-      u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-      u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+      u.x = pack_act2(v[8 * j + 0], v[8 * j + 1]);
+      u.y = pack_act2(v[8 * j + 2], v[8 * j + 3]);
+      u.z = pack_act2(v[8 * j + 4], v[8 * j + 5]);
+      u.w = pack_act2(v[8 * j + 6], v[8 * j + 7]);
       o[j] = u;
     }
   } else {
@@ -182,8 +183,8 @@ TASTE_DEVINL void epilogue_chunk_f32_coalesced(const uint32_t (&acc)[32], const 
       // bf16 copy of the new fp32 row (the next GEMM's A operand) and this lane's share of the row statistics
       if (row_ok) {
         uint2 u;
-        u.x = pack_bf16x2(x.x, x.y);
-        u.y = pack_bf16x2(x.z, x.w);
+        u.x = pack_act2(x.x, x.y);
+        u.y = pack_act2(x.z, x.w);
         *reinterpret_cast<uint2*>(p.out_bf16 + (grow0 + R) * p.ldc + n0 + j * 4) = u;
       }
       psum[i] += (x.x + x.y) + (x.z + x.w);          // this lane's 4 columns; lanes are combined once per tile
@@ -232,7 +233,7 @@ TASTE_DEVINL void epilogue_pack_bf16(const uint32_t (&acc)[32], const GemmParams
     for (int j = 0; j < 16; ++j) gelu_erf_pair(v[2 * j], v[2 * j + 1], v[2 * j], v[2 * j + 1]);
   }
 #pragma unroll
-  for (int j = 0; j < 16; ++j) out16[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+  for (int j = 0; j < 16; ++j) out16[j] = pack_act2(v[2 * j], v[2 * j + 1]);
 }
 
 TASTE_DEVINL void epilogue_store_bf16_coalesced(const uint32_t (&lo)[16], const uint32_t (&hi)[16], const GemmParams& p,
@@ -329,7 +330,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = umma_idesc(BM, BN, /*bf16*/ 1, 0, 0);
+    const uint32_t idesc = umma_idesc(BM, BN, p.ab_bf16, 0, 0);            // operand format: runtime (the DFT is always bf16)
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
@@ -502,7 +503,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const _
   } else if (warp == 1) {
     if (leader) {
       // ===================== MMA issuer (leader CTA only) =====================
-      constexpr uint32_t idesc = umma_idesc(2 * BM, BN2, /*bf16*/ 1, 0, 0);
+      const uint32_t idesc = umma_idesc(2 * BM, BN2, p.ab_bf16, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -771,13 +772,14 @@ int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
   const int64_t tiles256 = (d.n % 256 == 0) ? int64_t(m_tiles) * d.batches * (d.n / 256) : 0;
   const int bn = use_pair ? 128 /* B box: this CTA's half of the 256 columns */ : ((tiles256 >= num_sms()) ? 256 : 128);
 
+  const int ab_bf16 = d.ab_bf16 < 0 ? kActBf16 : d.ab_bf16;
   CUtensorMap ta, tb;
   {
     cuuint64_t dims[4] = {(cuuint64_t)d.k_inner, (cuuint64_t)d.s_count, (cuuint64_t)d.rows_in, (cuuint64_t)d.batches};
     cuuint64_t strides[3] = {(cuuint64_t)d.s_stride, (cuuint64_t)d.r_stride, (cuuint64_t)d.b_stride};
     cuuint32_t box[4] = {BK, 1, BM, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d.a), dims, strides, box, estr,
+    CUresult r = enc(&ta, ab_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(d.a), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error((int)r, "gemm: tensor map A encode failed (%d)", (int)r);
@@ -788,7 +790,7 @@ int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
     cuuint64_t strides[1] = {(cuuint64_t)(ktot * 2)};
     cuuint32_t box[2] = {BK, (cuuint32_t)bn};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d.w), dims, strides, box, estr,
+    CUresult r = enc(&tb, ab_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d.w), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error((int)r, "gemm: tensor map B encode failed (%d)", (int)r);
@@ -814,6 +816,7 @@ int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
   p.ln_colsum = d.ln_colsum;
   p.stats_out = d.stats_out;
   p.out_bf16 = static_cast<__nv_bfloat16*>(d.out_bf16);
+  p.ab_bf16 = ab_bf16;
   p.kclass = d.kclass;
   p.alg_bytes = d.alg_bytes;
   if (use_pair) return launch_epi2(ta, tb, p, d.epilogue, ln, stream);

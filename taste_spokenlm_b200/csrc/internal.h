@@ -1,5 +1,8 @@
 // Host-side internal interfaces between the translation units of libtaste_b200.so.
 #pragma once
+#ifndef TASTE_F16
+#define TASTE_F16 0          /* library flavour: see common.cuh */
+#endif
 #include <cuda_runtime.h>
 #include <cuda.h>
 #include <stddef.h>
@@ -75,6 +78,7 @@ struct GemmDesc {
   float* stats_out = nullptr;         // producer: [rows][n/128][2]; requires out_bf16
   void* out_bf16 = nullptr;
   bool force_pair = false;
+  int ab_bf16 = -1;                   // operand format: -1 = the library flavour (kActBf16), 1 = bf16 (the log-mel DFT)
   // accounting (prof.cu): kernel class and, when >= 0, the algorithmic bytes booked on this launch
   int kclass = KC_GEMM;
   double alg_bytes = -1.0;

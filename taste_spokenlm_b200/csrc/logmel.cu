@@ -204,8 +204,8 @@ logmel_split_kernel(const float* __restrict__ wav, const int32_t* __restrict__ n
       x[t] = i < TASTE_N_SAMPLES + TASTE_N_FFT ? padded_sample(w, n_valid, i) : 0.f;
       h[t] = __bfloat162float(__float2bfloat16_rn(x[t]));
     }
-    hi[e] = pack_bf16x2(h[0], h[1]);
-    lo[e] = pack_bf16x2(x[0] - h[0], x[1] - h[1]);
+    hi[e] = pack_true_bf16x2(h[0], h[1]);
+    lo[e] = pack_true_bf16x2(x[0] - h[0], x[1] - h[1]);
   }
   __nv_bfloat16* p0 = planes + int64_t(b) * 2 * LOGMEL_PLANE + i0;
   *reinterpret_cast<uint4*>(p0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -293,8 +293,8 @@ logmel_finish_kernel(const float* __restrict__ logspec, const unsigned int* __re
     if (out_f32) reinterpret_cast<float4*>(out_f32 + base)[i] = v;
     if (out_bf16) {
       uint2 u;
-      u.x = pack_bf16x2(v.x, v.y);
-      u.y = pack_bf16x2(v.z, v.w);
+      u.x = pack_act2(v.x, v.y);
+      u.y = pack_act2(v.z, v.w);
       reinterpret_cast<uint2*>(out_bf16 + base)[i] = u;
     }
   }
@@ -344,6 +344,7 @@ int launch_logmel(const taste_weights_t& w, const float* wav, const int32_t* n_s
     d.taps = 3;                                        // K slabs hi(x) | hi(x) | lo(x)  against  hi(t) | lo(t) | hi(t)
     d.tap_s[0] = 0, d.tap_s[1] = 0, d.tap_s[2] = 1;
     d.w = w.dft_w_bf16;
+    d.ab_bf16 = 1;                                     // split-bf16 planes and twiddles in both library flavours
     d.n = TASTE_DFT_N;
     d.out = scratch_spectrum;
     d.ldc = TASTE_DFT_N;

@@ -58,19 +58,27 @@ class _Workspace:
 
 
 class FrontendEngine:
-    """Log-mel tables + handle (no model weights).  Stands in for WhisperFrontend's state (WF:7-49)."""
+    """Log-mel tables + handle (no model weights).  Stands in for WhisperFrontend's state (WF:7-49).
 
-    def __init__(self, device):
+    `precision` ('bf16' default | 'fp16') selects the library flavour, i.e. the 16-bit type of the features handed to
+    the encoder stem; the DFT itself runs on split-bf16 planes in both."""
+
+    def __init__(self, device, precision=None):
         self.device = _require_cuda(device)
-        self.lib = _lib.load()
+        self.precision = _lib.resolve_precision(precision)
+        self.act_dtype = _lib.torch_dtype(self.precision)
+        self.lib = _lib.load(self.precision)
         self._keep: Dict[str, torch.Tensor] = {}
         self.w = _lib.Weights()
         self._fill_tables(self.w)
         self.w.dims = _lib.Dims(d_model=128, heads=2, ffn=128, enc_layers=0, dec_layers=0, vocab=1, max_target_pos=1,
                                 codebook_dim=256, codebook_size=512, num_quantizers=1, target_layer=0, reserved=0)
         self.handle = C.c_void_p()
-        _lib.check(self.lib.taste_handle_create(C.byref(self.w), C.byref(self.handle)), "taste_handle_create")
+        self._ck(self.lib.taste_handle_create(C.byref(self.w), C.byref(self.handle)), "taste_handle_create")
         self.ws = _Workspace(self.device)
+
+    def _ck(self, rc: int, what: str = ""):
+        _lib.check(rc, what, self.lib)
 
     def _dev(self, name: str, arr) -> C.c_void_p:
         t = torch.as_tensor(arr).contiguous().to(self.device)
@@ -104,11 +112,11 @@ class FrontendEngine:
         B = wav.shape[0]
         n_samples = n_samples.to(device=wav.device, dtype=torch.int32).contiguous()
         f32 = torch.empty(B, _lib.N_FRAMES, _lib.N_MELS, dtype=torch.float32, device=wav.device) if want_f32 else None
-        b16 = torch.empty(B, _lib.N_FRAMES, _lib.N_MELS, dtype=torch.bfloat16, device=wav.device) if want_bf16 else None
+        b16 = torch.empty(B, _lib.N_FRAMES, _lib.N_MELS, dtype=self.act_dtype, device=wav.device) if want_bf16 else None
         nbytes = self.lib.taste_ws_bytes(self.handle, B, 0)
         ws = self.ws.get(nbytes)
         stream = C.c_void_p(torch.cuda.current_stream(wav.device).cuda_stream)
-        _lib.check(self.lib.taste_logmel_f32(self.handle, _lib.ptr(wav), _lib.ptr(n_samples), B, wav.stride(0),
+        self._ck(self.lib.taste_logmel_f32(self.handle, _lib.ptr(wav), _lib.ptr(n_samples), B, wav.stride(0),
                                              _lib.ptr(f32), _lib.ptr(b16), _lib.ptr(ws), ws.numel(), stream),
                    "taste_logmel_f32")
         return f32, b16
@@ -117,10 +125,12 @@ class FrontendEngine:
 class TowerEngine(FrontendEngine):
     """Packed weights + handle for encoder, aggregator and RVQ (MT:33-211)."""
 
-    def __init__(self, cfg: TowerConfig, device):
+    def __init__(self, cfg: TowerConfig, device, precision=None):
         self.cfg = cfg
         self.device = _require_cuda(device)
-        self.lib = _lib.load()
+        self.precision = _lib.resolve_precision(precision)
+        self.act_dtype = _lib.torch_dtype(self.precision)
+        self.lib = _lib.load(self.precision)
         self._keep = {}
         self.handle = C.c_void_p()
         self.ws = _Workspace(self.device)
@@ -143,8 +153,8 @@ class TowerEngine(FrontendEngine):
         def f32(name, t):
             return self._dev(name, t.detach().to(device=dev, dtype=torch.float32))
 
-        def b16(name, t):
-            return self._dev(name, t.detach().to(device=dev, dtype=torch.float32).to(torch.bfloat16))
+        def b16(name, t):          # the flavour's 16-bit operand type (bf16 or fp16)
+            return self._dev(name, t.detach().to(device=dev, dtype=torch.float32).to(self.act_dtype))
 
         def qkv(prefix, p):
             wq = sd[p + "q_proj.weight"].detach().to(dev, torch.float32) * scale          # CW:342
@@ -228,14 +238,14 @@ class TowerEngine(FrontendEngine):
         self._pack_rvq(w, sd)
         self.w = w
         self._enc_arr, self._dec_arr = enc, dec
-        _lib.check(self.lib.taste_handle_create(C.byref(w), C.byref(self.handle)), "taste_handle_create")
+        self._ck(self.lib.taste_handle_create(C.byref(w), C.byref(self.handle)), "taste_handle_create")
 
     def _fold_ln(self, L, key, which, w_f32, b_f32, gamma, beta):
         """Fill the `*_ln` fields of an encoder layer: Linear(LayerNorm(x)) = rstd * (x W'^T - mean * c) + b'."""
         dev = self.device
         g = gamma.detach().to(dev, torch.float32)
         bt = beta.detach().to(dev, torch.float32)
-        wf = (w_f32 * g[None, :]).to(torch.bfloat16)
+        wf = (w_f32 * g[None, :]).to(self.act_dtype)
         c = wf.float().sum(dim=1)                      # from the bf16-rounded W': what the tensor core multiplies
         bp = b_f32 + w_f32 @ bt
         names = ("wqkv_ln", "bqkv_ln", "cqkv_ln") if which == "qkv" else ("w1_ln", "b1_ln", "c1_ln")
@@ -268,13 +278,15 @@ class TowerEngine(FrontendEngine):
         """feats [B,3000,128] fp32 or bf16 on device -> (h_last, h_target) bf16 [B,1500,D].   JES:133-223"""
         B, D = feats.shape[0], self.cfg.d_model
         assert feats.is_cuda and feats.is_contiguous() and feats.shape[1:] == (_lib.N_FRAMES, _lib.N_MELS)
-        h_last = torch.empty(B, _lib.ENC_FRAMES, D, dtype=torch.bfloat16, device=feats.device)
+        h_last = torch.empty(B, _lib.ENC_FRAMES, D, dtype=self.act_dtype, device=feats.device)
         h_t = torch.empty_like(h_last)
         ws = self._ws(B, 0)
         f32 = feats if feats.dtype == torch.float32 else None
-        b16 = feats if feats.dtype == torch.bfloat16 else None
-        assert f32 is not None or b16 is not None
-        _lib.check(self.lib.taste_encoder_fwd(self.handle, _lib.ptr(f32), _lib.ptr(b16), B, _lib.ptr(h_last),
+        b16 = feats if feats.dtype == self.act_dtype else None
+        if f32 is None and b16 is None:
+            raise _lib.TasteError(f"encoder features must be fp32 or {self.act_dtype} (this engine's precision is "
+                                  f"{self.precision}), got {feats.dtype}")
+        self._ck(self.lib.taste_encoder_fwd(self.handle, _lib.ptr(f32), _lib.ptr(b16), B, _lib.ptr(h_last),
                                               _lib.ptr(h_t), _lib.ptr(ws), ws.numel(), self._stream()),
                    "taste_encoder_fwd")
         return h_last, h_t
@@ -300,7 +312,7 @@ class TowerEngine(FrontendEngine):
         B, D = h_last.shape[0], self.cfg.d_model
         out = torch.empty(sum_tokens, D, dtype=torch.float32, device=h_last.device)
         ws = self._ws(B, sum_tokens)
-        _lib.check(self.lib.taste_aggregator_fwd(self.handle, _lib.ptr(h_last), _lib.ptr(h_t), _lib.ptr(tokens_packed),
+        self._ck(self.lib.taste_aggregator_fwd(self.handle, _lib.ptr(h_last), _lib.ptr(h_t), _lib.ptr(tokens_packed),
                                                  _lib.ptr(cu_tokens), B, sum_tokens, max_tokens, _lib.ptr(out),
                                                  _lib.ptr(ws), ws.numel(), self._stream()), "taste_aggregator_fwd")
         return out
@@ -308,7 +320,7 @@ class TowerEngine(FrontendEngine):
     @_on_device
     def word_pool(self, dec_out, cu_tokens, word_ids, lengths, B, Tmax) -> torch.Tensor:
         z = torch.empty(B, Tmax, self.cfg.d_model, dtype=torch.float32, device=dec_out.device)
-        _lib.check(self.lib.taste_word_pool_f32(_lib.ptr(dec_out), _lib.ptr(cu_tokens), _lib.ptr(word_ids),
+        self._ck(self.lib.taste_word_pool_f32(_lib.ptr(dec_out), _lib.ptr(cu_tokens), _lib.ptr(word_ids),
                                                 _lib.ptr(lengths), B, Tmax, self.cfg.d_model, _lib.ptr(z),
                                                 self._stream()), "taste_word_pool_f32")
         return z
@@ -320,7 +332,7 @@ class TowerEngine(FrontendEngine):
         B, T, in_dim = z.shape
         idx = torch.empty(B, T, self.cfg.num_quantizers, dtype=torch.int64, device=z.device)
         qz = torch.empty(B, T, self.cfg.d_model, dtype=torch.float32, device=z.device) if want_quantized else None
-        _lib.check(self.lib.taste_rvq_encode_f32(self.handle, _lib.ptr(z), _lib.ptr(lengths), B, T, in_dim,
+        self._ck(self.lib.taste_rvq_encode_f32(self.handle, _lib.ptr(z), _lib.ptr(lengths), B, T, in_dim,
                                                  _lib.ptr(idx), _lib.ptr(qz), self._stream()), "taste_rvq_encode_f32")
         return qz, idx
 
@@ -331,7 +343,7 @@ class TowerEngine(FrontendEngine):
         flat = indices.reshape(-1, indices.shape[-1]).contiguous()
         out = torch.empty(flat.shape[0], self.cfg.d_model if project_out else self.cfg.codebook_dim,
                           dtype=torch.float32, device=indices.device)
-        _lib.check(self.lib.taste_rvq_decode_f32(self.handle, _lib.ptr(flat), flat.shape[0], 1 if project_out else 0,
+        self._ck(self.lib.taste_rvq_decode_f32(self.handle, _lib.ptr(flat), flat.shape[0], 1 if project_out else 0,
                                                  _lib.ptr(out), self._stream()), "taste_rvq_decode_f32")
         return out.reshape(*shape, out.shape[-1])
 
@@ -348,7 +360,7 @@ class TowerEngine(FrontendEngine):
         alen = asr_token_lengths.to(device=dev, dtype=torch.int32).contiguous()
         llen = llm_token_lengths.to(device=dev, dtype=torch.int32).contiguous()
         out = torch.empty(B, L, Q, dtype=torch.int64, device=dev)
-        _lib.check(self.lib.taste_map_to_llm_tokens(_lib.ptr(idx), _lib.ptr(awid), _lib.ptr(alen), _lib.ptr(lwid),
+        self._ck(self.lib.taste_map_to_llm_tokens(_lib.ptr(idx), _lib.ptr(awid), _lib.ptr(alen), _lib.ptr(lwid),
                                                     _lib.ptr(llen), B, T, L, Q, _lib.ptr(out), self._stream()),
                    "taste_map_to_llm_tokens")
         return out
@@ -358,7 +370,7 @@ class TowerEngine(FrontendEngine):
         """Packed assembled ids on the device (MT:144-152); see taste_assemble_tokens."""
         B, Tmax = ids_dev.shape
         tokens = torch.empty(sum_tokens, dtype=torch.int32, device=self.device)
-        _lib.check(self.lib.taste_assemble_tokens(_lib.ptr(ids_dev), _lib.ptr(lens32), _lib.ptr(cu), B, Tmax,
+        self._ck(self.lib.taste_assemble_tokens(_lib.ptr(ids_dev), _lib.ptr(lens32), _lib.ptr(cu), B, Tmax,
                                                   _lib.ptr(tokens), self._stream()), "taste_assemble_tokens")
         return tokens
 
@@ -409,7 +421,7 @@ class TowerEngine(FrontendEngine):
         elif feats.shape[1] > _lib.N_FRAMES:                                            # JES:169-172
             raise ValueError(f"Whisper expects the mel input features to be of length {_lib.N_FRAMES}, "
                              f"but found {feats.shape[1]}")
-        if feats.dtype not in (torch.float32, torch.bfloat16):
+        if feats.dtype not in (torch.float32, self.act_dtype):
             feats = feats.float()
         feats = feats.to(dev).contiguous()
         h_last, h_t = self.encode(feats)

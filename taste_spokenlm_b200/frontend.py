@@ -40,6 +40,7 @@ class WhisperFrontendB200(nn.Module):
             raise NotImplementedError("do_pad_trim=False is not used by TASTE (PT:166, DS:242)")
         self.do_pad_trim = do_pad_trim
         self.permute = permute
+        self.precision = _lib.resolve_precision(kwargs.get("precision"))   # 16-bit dtype of forward_device's features
         self._device_hint: Optional[torch.device] = None
         self._engine: Optional[FrontendEngine] = None
 
@@ -59,7 +60,7 @@ class WhisperFrontendB200(nn.Module):
         if device.type == "cuda" and device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
         if self._engine is None or self._engine.device != device:
-            self._engine = FrontendEngine(device)
+            self._engine = FrontendEngine(device, self.precision)
         return self._engine
 
     def forward_device(self, wav: torch.Tensor, n_samples: torch.Tensor, want_f32=True, want_bf16=False):

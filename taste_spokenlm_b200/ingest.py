@@ -119,7 +119,7 @@ class ResampleMeanB200:
         if device.type != "cuda" or not torch.cuda.is_available():
             raise TasteError("ResampleMeanB200 needs a CUDA device (there is no CPU fallback)")
         self.device = device
-        self.lib = _lib.load()
+        self.lib = _lib.load("bf16")          # the resampler is fp32 end to end: either flavour would do
         self.new_freq = int(new_freq)
         self.wav_stride = int(wav_stride)
         self._tables: Dict[int, Dict[str, object]] = {}

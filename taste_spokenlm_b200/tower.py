@@ -136,7 +136,7 @@ class WhisperAudioJointEncoderSegmenterB200(nn.Module):
         feats = audio_features.detach()
         if feats.shape[1] < _lib.N_FRAMES:
             feats = torch.nn.functional.pad(feats, (0, 0, 0, _lib.N_FRAMES - feats.shape[1]))
-        if feats.dtype not in (torch.float32, torch.bfloat16):
+        if feats.dtype not in (torch.float32, eng.act_dtype):
             feats = feats.float()
         h_last, h_t = eng.encode(feats.to(dev).contiguous())
         ids = whisper_text_token.detach()[:, 4:-1].to(device=dev, dtype=torch.int64).contiguous()
@@ -292,8 +292,13 @@ class TasteAudioTowerB200(nn.Module):
         kwargs_for_joint_encoder_segmenter: Dict = None,
         kwargs_for_quantizer: Dict = None,
         whisper_geometry: Dict = None,
+        precision: Optional[str] = None,
     ):
+        """`precision` (not a reference argument; default TASTE_PRECISION or 'bf16'): the library flavour, i.e. the
+        16-bit type of the tensor-core operands — 'bf16' (BASELINE config 2) or 'fp16' (the reference's own autocast
+        dtype, JES:133; 8x smaller operand rounding, the flavour that meets the >= 99.5 % index-agreement bar)."""
         super().__init__()
+        self.precision = _lib.resolve_precision(precision)
         if not is_joint_encoder_segmenter:
             raise NotImplementedError("only the joint encoder/segmenter tower (CFG:136) is on the B200 path")
         kj = dict(kwargs_for_joint_encoder_segmenter or {})
@@ -336,8 +341,9 @@ class TasteAudioTowerB200(nn.Module):
 
     # ---- construction helpers ----
     @classmethod
-    def from_config(cls, cfg: TowerConfig = FULL) -> "TasteAudioTowerB200":
+    def from_config(cls, cfg: TowerConfig = FULL, precision: Optional[str] = None) -> "TasteAudioTowerB200":
         return cls(
+            precision=precision,
             is_joint_encoder_segmenter=True, quantization_on=True, audio_embed_dim=cfg.d_model,
             kwargs_for_joint_encoder_segmenter=dict(dtype="bfloat16", forward_type="asr_attn_pooling", is_word_level=True,
                                                     make_v_proj_identity=True, model_name_or_path="", skip_prefix_idx=4,
@@ -389,14 +395,14 @@ class TasteAudioTowerB200(nn.Module):
         for t in self._sentinels:
             ver += t._version
             ptr ^= t.data_ptr()
-        return (self._state_epoch, str(self._sentinels[0].device), ver, ptr)
+        return (self._state_epoch, str(self._sentinels[0].device), ver, ptr, self.precision)
 
     def engine(self) -> TowerEngine:
         """Packed kernel-side weights; rebuilt when the state changed (see `_state_key`)."""
         key = self._state_key()
         if self._engine is None or key != self._engine_key:
             dev = next(self.parameters()).device
-            eng = TowerEngine(self.cfg, dev)
+            eng = TowerEngine(self.cfg, dev, self.precision)
             eng.pack(self.state_dict())
             self._engine, self._engine_key = eng, key
         return self._engine

@@ -16,11 +16,17 @@ torch.set_grad_enabled(False)
 def test_library_exports_every_declared_symbol(built_lib):
     declared = _lib.declared_symbols()
     assert len(declared) >= 18
-    for name in declared:
-        assert hasattr(built_lib, name), f"libtaste_b200.so does not export {name}"
     assert set(declared) == set(_lib._SIGS), "ctypes signature table out of sync with include/taste_b200.h"
-    assert built_lib.taste_abi_version() == 3
-    assert isinstance(built_lib.taste_launch_count(), int)
+    for flavour, code in (("bf16", 0), ("fp16", 1)):                 # both library flavours export the same ABI
+        lib = _lib.load(flavour)
+        for name in declared:
+            assert hasattr(lib, name), f"{flavour} library does not export {name}"
+        assert lib.taste_abi_version() == 4
+        assert lib.taste_operand_dtype() == code
+        assert isinstance(lib.taste_launch_count(), int)
+    assert _lib.load("bf16") is built_lib or _lib.resolve_precision() == "fp16"
+    with pytest.raises(_lib.TasteError):
+        _lib.load("int8")
 
 
 def test_argument_errors_without_a_gpu(built_lib):
