@@ -247,6 +247,12 @@ int taste_gemm_set_mode(int mode);
 /* y = LayerNorm(x) (eps 1e-5, CW:660): x fp32 [rows, d]; y bf16 (out_bf16 != 0) or fp32. */
 int taste_layernorm_f32(const float* x, const float* w, const float* b, void* y, int rows, int d, int out_bf16,
                         void* stream);
+/* The aggregator's cross-attention (CW:361-366 with the dict K/V of JES:377-388): ragged queries against fixed-length keys,
+ * no mask.  q / o are PACKED [total_q, ld] matrices, utterance b owning rows cu_q[b] .. cu_q[b+1] (at most max_q_len of
+ * them); k / v are [batch * kv_len, ld].  Runs on the tcgen05 / TMA attention kernel (one 128-query tile per work item). */
+int taste_attention_ragged_bf16(const void* q, const void* k, const void* v, void* o, int ldq, int ldk, int ldv, int ldo,
+                                const int32_t* cu_q, int total_q, int max_q_len, int kv_len, int batch, int heads,
+                                void* stream);
 /* softmax(Q K^T [+ causal mask]) V per head (CW:377-394); q is expected pre-scaled.  bf16, head_dim 64.
  * Row b of q/o starts at cu_q[b] (or b*q_len if cu_q is NULL) and has cu_q[b+1]-cu_q[b] (or q_len) rows; same
  * for k/v with cu_kv / kv_len.  ld* are row strides in elements. */

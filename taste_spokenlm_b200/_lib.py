@@ -90,6 +90,8 @@ _SIGS = {
     "taste_attention_set_mode": (C.c_int, [C.c_int]),
     "taste_gemm_set_mode": (C.c_int, [C.c_int]),
     "taste_layernorm_f32": (C.c_int, [p, p, p, p, C.c_int, C.c_int, C.c_int, p]),
+    "taste_attention_ragged_bf16": (C.c_int, [p, p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, p, C.c_int, C.c_int, C.c_int,
+                                              C.c_int, C.c_int, p]),
     "taste_attention_bf16": (C.c_int, [p, p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, p, p, C.c_int, C.c_int,
                                        C.c_int, C.c_int, C.c_int, p]),
 }

@@ -486,6 +486,20 @@ int taste_layernorm_f32(const float* x, const float* w, const float* b, void* y,
   return launch_layernorm(x, w, b, y, rows, d, out_bf16 != 0, static_cast<cudaStream_t>(stream));
 }
 
+int taste_attention_ragged_bf16(const void* q, const void* k, const void* v, void* o, int ldq, int ldk, int ldv, int ldo,
+                                const int32_t* cu_q, int total_q, int max_q_len, int kv_len, int batch, int heads,
+                                void* stream) {
+  if (!cu_q || total_q <= 0) return set_error(TASTE_E_ARG, "attention_ragged: cu_q and total_q are required");
+  AttnDesc at;
+  at.q = q; at.k = k; at.v = v; at.o = o;
+  at.ldq = ldq; at.ldk = ldk; at.ldv = ldv; at.ldo = ldo;
+  at.cu_q = cu_q; at.cu_kv = nullptr;
+  at.q_len = max_q_len; at.kv_len = kv_len;
+  at.batch = batch; at.heads = heads; at.causal = 0;
+  at.total_q = total_q;
+  return launch_attention(at, static_cast<cudaStream_t>(stream));
+}
+
 int taste_attention_bf16(const void* q, const void* k, const void* v, void* o, int ldq, int ldk, int ldv, int ldo,
                          const int32_t* cu_q, const int32_t* cu_kv, int q_len, int kv_len, int batch, int heads,
                          int causal, void* stream) {

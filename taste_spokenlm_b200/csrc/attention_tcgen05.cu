@@ -57,6 +57,8 @@ struct FaCfg {
   // TMEM columns: S_i fp32 [BK], O_i fp32 [64], P_i bf16 pairs [BK / 2]
   static constexpr uint32_t kColS = 0, kColO = NT * BK, kColP = NT * BK + NT * FA_HD;
   static constexpr int kSoftmaxRegs = NT == 2 ? 232 : 152;   // NT x 128 x regs + 128 x 40 <= 65 536
+  // NT = 1 (256 threads): every thread may keep up to 255 registers from launch, so no setmaxnreg hand-over is needed
+  static constexpr bool kMoveRegs = NT >= 2;
   static_assert(kColP + NT * BK / 2 <= 512, "TMEM");
   static_assert(kSmem <= 232448, "shared memory");
   static_assert((NT * 128 * kSoftmaxRegs + 128 * 40) <= 65536, "registers");
@@ -77,6 +79,13 @@ struct FaParams {
   long long* dbg;      // timeline trace (VAR bit 2 only)
   int q_len, kv_len;
   int heads, q_blocks, n_items;      // work item w = (b * heads + head) * q_blocks + qb
+  // Ragged queries (the aggregator's cross-attention, CW:361-366 with JES:377-388's dict K/V): utterance b owns the packed
+  // query / output rows cu_q[b] .. cu_q[b + 1]; keys and values stay [batch, kv_len].  Q tiles are fetched at their packed
+  // row (rows past the utterance belong to its neighbour or are out-of-bounds zeros: computed, never stored) and the
+  // output pass writes each thread's own row with plain stores, masked by the utterance's row count.
+  const int* cu_q;     // null = fixed q_len rows per utterance
+  uint16_t* o;         // ragged mode only
+  int ldo;
 };
 
 // Work item w = (b * heads + head) * q_blocks + qb, walked with stride gridDim.x.  The stride is decomposed once; each
@@ -188,8 +197,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
   // their exp2 phase far better with 232 registers (2 x 128; 152 for 3 x 64); the TMA / MMA warps need almost nothing.
   // 256 x 232 + 128 x 40 <= 384 x 168.  (The instruction sits at the head of each role's branch: ptxas budgets
   // registers per region it dominates.)
-#define FA_REGS_SMALL() asm volatile("setmaxnreg.dec.sync.aligned.u32 40;")
-#define FA_REGS_LARGE() asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::kSoftmaxRegs))
+#define FA_REGS_SMALL()                                                      \
+  do {                                                                       \
+    if constexpr (Cfg::kMoveRegs) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;"); \
+  } while (0)
+#define FA_REGS_LARGE()                                                      \
+  do {                                                                       \
+    if constexpr (Cfg::kMoveRegs) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::kSoftmaxRegs)); \
+  } while (0)
   if (warp > kMmaWarp0 + NT - 1) {
     FA_REGS_SMALL();        // idle: only completes the last warpgroup
   } else if (warp == kTmaWarp) {
@@ -203,13 +218,15 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
       const int b = walk.b;
       const int q0 = walk.qb * (NT * FA_BQ);
       const int qbuf = it & 1;
+      const int q_row0 = p.cu_q ? __ldg(p.cu_q + b) : 0;      // ragged: packed rows, one "batch" entry
+      const int q_b = p.cu_q ? 0 : b;
       mbar_wait_relaxed(&q_empty[qbuf], uint32_t(((it >> 1) & 1) ^ 1));
       if (elect_one()) {
         uint8_t* sq = sQ + size_t(NT * qbuf) * FA_TILE_BYTES;
         mbar_expect_tx(&q_full[qbuf], NT * FA_TILE_BYTES);
 #pragma unroll
         for (int t = 0; t < NT; ++t)
-          tma_load_3d(sq + size_t(t) * FA_TILE_BYTES, &tma_q, &q_full[qbuf], head * FA_HD, q0 + t * FA_BQ, b);
+          tma_load_3d(sq + size_t(t) * FA_TILE_BYTES, &tma_q, &q_full[qbuf], head * FA_HD, q_row0 + q0 + t * FA_BQ, q_b);
       }
       __syncwarp();
       for (int j = 0; j < n_blocks; ++j) {
@@ -344,6 +361,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
     // ---- output of a finished item: O_i / l (called once the item's last P V may be waited for; g = blocks done) ----
     float out_inv = 0.f;
     int out_head = 0, out_b = 0, out_row = 0, out_it = 0;
+    int out_row0 = 0, out_rows_valid = 0;      // ragged mode: first packed row and row count of the utterance
     auto write_output = [&]() {
       // Thread-per-row global stores (32 rows x 16 B per instruction) cost ~2 cycles per 16-byte request: 1900 cycles
       // per item on the in-kernel timeline, 12 % of the kernel.  Each warp now stages its 32 x 64 bf16 tile in shared
@@ -353,6 +371,29 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
       FA_TRACE(4 + i, out_it * 8 + 0);
       tc_fence_after();
       const float inv = out_inv;
+      if (p.cu_q) {
+        // ragged: this thread's row straight from TMEM to global memory (128 B per row), masked by the utterance's rows
+#pragma unroll
+        for (int hc = 0; hc < 2; ++hc) {
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(t_o + uint32_t(hc * 32), o);
+          tmem_ld_wait();
+          if (out_row < out_rows_valid) {
+            uint4* dst = reinterpret_cast<uint4*>(p.o + (int64_t(out_row0) + out_row) * p.ldo + out_head * FA_HD + hc * 32);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              uint4 u;
+              u.x = pack_act2(__uint_as_float(o[8 * e + 0]) * inv, __uint_as_float(o[8 * e + 1]) * inv);
+              u.y = pack_act2(__uint_as_float(o[8 * e + 2]) * inv, __uint_as_float(o[8 * e + 3]) * inv);
+              u.z = pack_act2(__uint_as_float(o[8 * e + 4]) * inv, __uint_as_float(o[8 * e + 5]) * inv);
+              u.w = pack_act2(__uint_as_float(o[8 * e + 6]) * inv, __uint_as_float(o[8 * e + 7]) * inv);
+              dst[e] = u;
+            }
+          }
+        }
+        tc_fence_before();
+        return;
+      }
       uint8_t* stage_out = sOut + size_t(warp) * FA_OUT_BYTES;
       if (lane == 0) tma_store_wait_read();          // the previous item's store has read the staging tile
       __syncwarp();
@@ -594,6 +635,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
       out_b = b;
       out_row = row;
       out_it = it;
+      if (p.cu_q) {
+        out_row0 = __ldg(p.cu_q + b);
+        out_rows_valid = __ldg(p.cu_q + b + 1) - out_row0;
+      }
       write_output();
     }
     if (lane == 0) tma_store_wait_all();
@@ -620,84 +665,75 @@ static int make_map(EncodeTiledFn enc, CUtensorMap* m, const void* base, int hea
   return 0;
 }
 
-static long long* g_fa_trace = nullptr;
-extern "C" void taste_dbg_attention_trace(void* dev_buf) { g_fa_trace = static_cast<long long*>(dev_buf); }
+// Per-device launch state, resolved once (cudaFuncSetAttribute and the SM count are per device).
+struct FaDevice {
+  bool configured = false;
+  int n_sm = 0;
+};
+static FaDevice g_fa_dev[kMaxDevices];
+
+// Which instantiation serves a problem.  The geometry was chosen by measurement and is resolved here
+// from the problem alone: no environment lookups on the launch path.
+//   encoder self-attention, >= 384 queries : 3 tiles x 64 keys, free-running, 4 of 16 exp2 pairs on the FMA pipe
+//   fixed-length, 256 .. 383 queries       : 2 tiles x 128 keys, split phases under ping-pong turns, 5 of 16
+//   ragged queries (aggregator cross-attn) : 1 tile x 128 keys (utterances have <= 448 query rows, typically ~70)
+#define FA_VARIANTS(X) X(FA_VAR_FREE, 4, 3, 64) X(FA_VAR_SPLIT, 5, 2, 128) X(FA_VAR_FREE, 4, 1, 128)
 
 bool attention_tcgen05_eligible(const AttnDesc& d) {
-  if (d.cu_q || d.cu_kv || d.causal) return false;
-  if (d.q_len < 2 * FA_BQ || d.kv_len < 128) return false;             // small problems: the mma.sync kernel
+  if (d.cu_kv || d.causal) return false;                                // causal / ragged keys: the mma.sync kernel
+  if (d.kv_len < 128) return false;
+  if (!d.cu_q && d.q_len < 2 * FA_BQ) return false;                     // small fixed-length problems: the mma.sync kernel
   if ((reinterpret_cast<uintptr_t>(d.q) | reinterpret_cast<uintptr_t>(d.k) | reinterpret_cast<uintptr_t>(d.v) |
        reinterpret_cast<uintptr_t>(d.o)) & 15)
     return false;
   if ((d.ldq | d.ldk | d.ldv | d.ldo) % 8 != 0) return false;
+  if (d.cu_q && d.total_q <= 0) return false;                           // ragged mode needs the packed row count
   return true;
 }
 
 int launch_attention_tcgen05(const AttnDesc& d, cudaStream_t stream) {
   EncodeTiledFn enc = get_tensor_map_encoder();
   if (!enc) return set_error(TASTE_E_NO_DEVICE, "cuTensorMapEncodeTiled entry point unavailable");
-  // Compiled variants (VAR, POLY, NT, BK).  Default: split exp2 phases, 5 polynomial pairs of 16, 2 tiles x 128 keys.
-  // The others are A/B knobs: TASTE_FA_VAR, TASTE_FA_POLY, TASTE_FA_TILES ("3x64").
-#define FA_VARIANTS(X)                                                                                          \
-  X(FA_VAR_FREE, 4, 3, 64) X(FA_VAR_FREE, 6, 3, 64) X(FA_VAR_FREE, 0, 3, 64) X(FA_VAR_SPLIT, 5, 3, 64)          \
-  X(FA_VAR_FREE | 128, 6, 3, 64) X(FA_VAR_SPLIT, 5, 2, 64)                                                      \
-  X(FA_VAR_SPLIT, 5, 2, 128) X(FA_VAR_SPLIT, 6, 2, 128) X(FA_VAR_SPLIT | 4, 5, 2, 128)                          \
-  X(FA_VAR_SPLIT | 256, 5, 2, 128) X(FA_VAR_INTERLEAVED, 6, 2, 128) X(FA_VAR_INTERLEAVED, 0, 2, 128)            \
-  X(FA_VAR_SPEC, 5, 2, 128) X(FA_VAR_SPEC | 4, 5, 2, 128)                                                       \
-  X(FA_VAR_SPLIT | 16, 5, 2, 128) X(FA_VAR_INTERLEAVED | 16, 6, 2, 128)
-  static bool configured = false;
-  if (!configured) {
+  const int dev = current_device();
+  FaDevice& fd = g_fa_dev[dev];
+  if (!fd.configured) {
 #define FA_CFG(V, P, T, K)                                                                                         \
   TASTE_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<(V), (P), T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      (int)FaCfg<T, K>::kSmem));
     FA_VARIANTS(FA_CFG)
 #undef FA_CFG
-    configured = true;
+    cudaDeviceGetAttribute(&fd.n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (fd.n_sm <= 0) fd.n_sm = 148;
+    fd.configured = true;
   }
-  const char* ev = getenv("TASTE_FA_VAR");
-  const char* ep = getenv("TASTE_FA_POLY");          // "0" = every exponential on the MUFU
-  const char* et = getenv("TASTE_FA_TILES");
-  // default: 3 tiles x 64 keys, free-running, 4 of 16 pairs on the FMA pipe (0.95 ms per encoder layer against 1.00 ms
-  // for the best 2 x 128 variant: split phases under the ping-pong turn, 5 of 16).  With any knob set, the others
-  // default to the 2 x 128 family.
-  const bool knobs = ev || ep || et;
-  int want_var = ev ? atoi(ev) : (knobs ? FA_VAR_SPLIT : FA_VAR_FREE);
-  int want_poly = ep ? atoi(ep) : (knobs ? ((want_var & 64) ? 5 : 6) : 4);
-  int want_nt = knobs ? 2 : 3, want_bk = knobs ? 128 : 64;
-  if (et && sscanf(et, "%dx%d", &want_nt, &want_bk) != 2) return set_error(TASTE_E_ARG, "TASTE_FA_TILES: expected <tiles>x<keys>");
-  if (d.q_len < want_nt * FA_BQ) {                                     // short sequences: two tiles
-    if (!knobs) want_var = FA_VAR_SPLIT, want_poly = 5;
-    want_nt = 2, want_bk = 128;
-  }
+  const bool ragged = d.cu_q != nullptr;
+  int want_var = FA_VAR_FREE, want_poly = 4, want_nt = 3, want_bk = 64;
+  if (ragged) want_nt = 1, want_bk = 128;
+  else if (d.q_len < 3 * FA_BQ) want_var = FA_VAR_SPLIT, want_poly = 5, want_nt = 2, want_bk = 128;
   CUtensorMap mq, mk, mv, mo;
   int rc;
-  if ((rc = make_map(enc, &mq, d.q, d.heads, d.q_len, d.batch, d.ldq))) return rc;
+  // ragged queries / outputs: one packed [total_q, heads * 64] matrix (a single "batch" entry)
+  const int q_rows = ragged ? d.total_q : d.q_len, q_batch = ragged ? 1 : d.batch;
+  if ((rc = make_map(enc, &mq, d.q, d.heads, q_rows, q_batch, d.ldq))) return rc;
   if ((rc = make_map(enc, &mk, d.k, d.heads, d.kv_len, d.batch, d.ldk, want_bk))) return rc;
   if ((rc = make_map(enc, &mv, d.v, d.heads, d.kv_len, d.batch, d.ldv, want_bk))) return rc;
-  if ((rc = make_map(enc, &mo, d.o, d.heads, d.q_len, d.batch, d.ldo, 32))) return rc;      // one warp's rows per store
+  if ((rc = make_map(enc, &mo, d.o, d.heads, q_rows, q_batch, d.ldo, 32))) return rc;      // one warp's rows per store
   FaParams p;
-  p.dbg = g_fa_trace;
+  p.dbg = nullptr;
   p.q_len = d.q_len;
   p.kv_len = d.kv_len;
   p.heads = d.heads;
   p.q_blocks = (d.q_len + want_nt * FA_BQ - 1) / (want_nt * FA_BQ);
   p.n_items = p.q_blocks * d.heads * d.batch;
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (n_sm <= 0) n_sm = 148;
-  }
-  int n_cta = p.n_items < n_sm ? p.n_items : n_sm;
-  if (const char* lim = getenv("TASTE_FA_MAX_CTAS")) {         // co-scheduling probe (scripts/coschedule_probe.py)
-    const int v = atoi(lim);
-    if (v > 0 && v < n_cta) n_cta = v;
-  }
+  p.cu_q = d.cu_q;
+  p.o = static_cast<uint16_t*>(d.o);
+  p.ldo = d.ldo;
+  const int n_cta = p.n_items < fd.n_sm ? p.n_items : fd.n_sm;
   dim3 grid(n_cta);
-  const double pairs = double(d.batch) * d.q_len * d.kv_len;
-  ProfScope ps(stream, d.kclass == KC_ATTN_ENC ? KC_ATTN_ENC : KC_ATTN_TC, 4.0 * pairs * FA_HD * d.heads,
-               2.0 * FA_HD * d.heads * double(d.batch) * (2.0 * d.q_len + 2.0 * d.kv_len));
+  const double tq = ragged ? double(d.total_q) : double(d.batch) * d.q_len;
+  ProfScope ps(stream, d.kclass == KC_ATTN_ENC ? KC_ATTN_ENC : (ragged ? KC_ATTN_AGG : KC_ATTN_TC),
+               4.0 * tq * d.kv_len * FA_HD * d.heads,
+               2.0 * FA_HD * d.heads * (2.0 * tq + 2.0 * double(d.batch) * d.kv_len));
   bool launched = false;
 #define FA_GO(V, P, T, K)                                                                                           \
   if (!launched && want_var == (V) && want_poly == (P) && want_nt == T && want_bk == K) {                            \

@@ -647,21 +647,22 @@ EncodeTiledFn get_tensor_map_encoder() {
   return fn;
 }
 
+// Launch state is cached per device ordinal: shared-memory attributes and occupancy belong to the CURRENT device.
 static int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[kMaxDevices] = {};
+  const int dev = current_device();
+  if (n[dev] == 0) {
+    cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (n[dev] <= 0) n[dev] = 148;
   }
-  return n;
+  return n[dev];
 }
 
 template <int BN, int EPI>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   auto kern = gemm_bf16_tcgen05_kernel<BN, EPI>;
-  static bool configured = false;
+  static bool configured_dev[kMaxDevices] = {};
+  bool& configured = configured_dev[current_device()];
   if (!configured) {
     TASTE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmCfg<BN>::kSmemBytes));
     configured = true;
@@ -679,7 +680,8 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
 template <int EPI, int LN>
 static int launch_cfg2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   auto kern = gemm_bf16_tcgen05_2cta_kernel<EPI, LN>;
-  static int max_pairs = 0;
+  static int max_pairs_dev[kMaxDevices] = {};
+  int& max_pairs = max_pairs_dev[current_device()];
   if (max_pairs == 0) {
     TASTE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gemm2Cfg::kSmemBytes));
     cudaLaunchConfig_t cfg = {};
@@ -700,10 +702,6 @@ static int launch_cfg2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     if (getenv("TASTE_DEBUG")) fprintf(stderr, "[taste] gemm pair kernel: %d co-resident CTA pairs\n", n);
   }
   int pairs = p.total_tiles < max_pairs ? p.total_tiles : max_pairs;
-  if (const char* lim = getenv("TASTE_GEMM_MAX_PAIRS")) {      // co-scheduling probe (scripts/coschedule_probe.py)
-    const int v = atoi(lim);
-    if (v > 0 && v < pairs) pairs = v;
-  }
   const double m = double(p.rows_out) * (p.total_tiles / (p.n_tiles * p.m_tiles_per_batch));
   const double n = double(p.n_tiles) * BN2, k = double(p.taps) * p.kb_per_tap * BK;
   const double out_b = (EPI == EPI_BF16 || EPI == EPI_GELU_BF16) ? 2.0 : (EPI == EPI_RESID_F32 ? 8.0 : 4.0);

@@ -12,6 +12,14 @@
 
 namespace taste {
 
+// Per-device caches (cudaFuncSetAttribute, occupancy, SM count) are indexed by the current device ordinal.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < kMaxDevices) ? d : 0;
+}
+
 // ---- error plumbing (api.cu) ----
 int set_error(int code, const char* fmt, ...);
 #define TASTE_CUDA_OK(expr)                                                                        \

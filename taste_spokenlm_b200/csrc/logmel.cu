@@ -310,7 +310,8 @@ int launch_logmel(const taste_weights_t& w, const float* wav, const int32_t* n_s
   if (!w.dft_cos || !w.dft_sin || !w.hann || !w.mel_start || !w.mel_count || !w.mel_weight)
     return set_error(TASTE_E_ARG, "logmel: tables missing from the handle");
   if (batch <= 0) return 0;
-  static bool configured = false;
+  static bool configured_dev[kMaxDevices] = {};
+  bool& configured = configured_dev[current_device()];
   if (!configured) {
     TASTE_CUDA_OK(cudaFuncSetAttribute(logmel_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_SMEM));
     configured = true;

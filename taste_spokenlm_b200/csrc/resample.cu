@@ -116,7 +116,9 @@ int launch_resample_mean(const float* in, const int64_t* in_off, const int32_t* 
   p.wav = wav; p.wav_stride = wav_stride; p.n_out = n_out;
   const size_t smem = (size_t((nw * knz_ld + 3) & ~3) + p.span + nw) * sizeof(float);
   if (smem > 200 * 1024) return set_error(TASTE_E_SHAPE, "resample: tap table needs %zu bytes of shared memory", smem);
-  static size_t configured = 48 * 1024;
+  static size_t configured_dev[kMaxDevices] = {};
+  size_t& configured = configured_dev[current_device()];
+  if (configured == 0) configured = 48 * 1024;
   if (smem > configured) {
     TASTE_CUDA_OK(cudaFuncSetAttribute(resample_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;

@@ -199,37 +199,24 @@ def test_attention_fixed(lib, B, S, H, mode):
     assert _rel(o.float(), ref) < 6e-3          # bf16 P and bf16 output rounding
 
 
-@pytest.mark.parametrize("variant", [None, (16, 6, "3x64"), (144, 6, "3x64"), (64, 5, "3x64"), (64, 5, "2x64"), (64, 5), (64, 6),
-                                     (320, 5), (192, 5), (80, 5), (0, 6), (0, 0)])
+@pytest.mark.parametrize("S", [1500, 300])                   # 3 x 64 free-running tiles / 2 x 128 ping-pong tiles
 @pytest.mark.parametrize("jump", [0.0, 30.0, 250.0])
-def test_attention_score_range(lib, variant, jump, monkeypatch):
-    """Encoder kernel variants (TASTE_FA_VAR / TASTE_FA_POLY) on rows whose scores GROW along the key axis: later key
-    blocks exceed the running maximum by `jump` natural units.  30 stays inside the fp32 range of the stale-reference
-    exponentials; 250 overflows it and must take the exact path (maximum, rescale, second pass).  Some queries also
-    see strongly negative scores (argument clamp of the polynomial exp2)."""
-    if variant is not None:
-        monkeypatch.setenv("TASTE_FA_VAR", str(variant[0]))
-        monkeypatch.setenv("TASTE_FA_POLY", str(variant[1]))
-        if len(variant) > 2:
-            monkeypatch.setenv("TASTE_FA_TILES", variant[2])
-        else:
-            monkeypatch.delenv("TASTE_FA_TILES", raising=False)
-    else:
-        monkeypatch.delenv("TASTE_FA_TILES", raising=False)
-        monkeypatch.delenv("TASTE_FA_VAR", raising=False)
-        monkeypatch.delenv("TASTE_FA_POLY", raising=False)
+def test_attention_score_range(lib, S, jump):
+    """Encoder kernel on rows whose scores GROW along the key axis: later key blocks exceed the running maximum by `jump`
+    natural units (lazy rescale: the stale maximum may lag by up to 2^8).  Some queries also see strongly negative scores
+    (argument range of the polynomial exp2)."""
     torch.manual_seed(11)
-    B, S, H = 2, 1500, 2
+    B, H = 2, 2
     D = H * 64
     qkv = (torch.randn(B * S, 3 * D, device="cuda") * 0.7)
     q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
     # a shared direction: score offset = qa * kb[key]; kb steps up across the 128-key blocks
     pos = torch.arange(S, device="cuda").repeat(B)
     step = torch.zeros(B * S, device="cuda")
-    step[pos >= 300] = 0.2
-    step[pos >= 700] = 0.5
-    step[pos >= 1100] = 1.0
-    step[pos >= 1400] = 0.6                   # and down again: the last block must not dominate
+    step[pos >= S // 5] = 0.2
+    step[pos >= S // 2] = 0.5
+    step[pos >= (3 * S) // 4] = 1.0
+    step[pos >= (14 * S) // 15] = 0.6         # and down again: the last block must not dominate
     qa = torch.full((B * S,), 4.0, device="cuda")
     qa[::7] = -4.0                            # these queries prefer the EARLY keys (later scores strongly negative)
     for h in range(H):
@@ -274,6 +261,46 @@ def test_attention_ragged(lib, causal):
         vb = v[ks:ks + kvlens[b]].float().view(-1, H, 64).transpose(0, 1)
         ref = _attn_ref(qb, kb, vb, bool(causal)).transpose(0, 1).reshape(qlens[b], D)
         assert _rel(o[qs:qs + qlens[b]].float(), ref) < 6e-3, b
+
+
+@pytest.mark.parametrize("qlens,kv", [([69, 5, 130, 448, 1, 128, 129], 1500), ([70] * 40, 1500), ([33, 200], 200),
+                                      ([448, 447, 3], 129)])
+def test_attention_ragged_cross_tcgen05(lib, qlens, kv):
+    """The aggregator's cross-attention (ragged packed queries, fixed-length keys, no mask) on the tcgen05 / TMA kernel
+    (one 128-query tile per work item), against an fp64 statement and the mma.sync kernel; guard rows around the packed
+    output catch stores past an utterance's last row."""
+    torch.manual_seed(len(qlens) * 7 + kv)
+    H = 3
+    D = H * 64
+    B, total = len(qlens), sum(qlens)
+    cu_q = torch.tensor([0] + list(np.cumsum(qlens)), dtype=torch.int32, device="cuda")
+    q = (torch.randn(total, D, device="cuda") * 0.7).bfloat16()
+    k = (torch.randn(B * kv, D, device="cuda") * 0.7).bfloat16()
+    v = torch.randn(B * kv, D, device="cuda").bfloat16()
+    obuf = torch.full((total + 64, D), float("nan"), device="cuda").bfloat16()
+    obuf[:32] = 7.0
+    obuf[32 + total:] = 7.0
+    o = obuf[32:32 + total]
+    n0 = lib.taste_launch_count()
+    _lib.check(lib.taste_attention_ragged_bf16(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(o), D, D, D, D, _lib.ptr(cu_q),
+                                               total, max(qlens), kv, B, H, _stream()), "attn ragged")
+    torch.cuda.synchronize()
+    assert lib.taste_launch_count() == n0 + 1
+    assert bool((obuf[:32] == 7.0).all()) and bool((obuf[32 + total:] == 7.0).all()), "store outside the packed rows"
+    assert torch.isfinite(o.float()).all()
+    o2 = torch.full_like(o, float("nan"))
+    assert lib.taste_attention_set_mode(1) == 0
+    _lib.check(lib.taste_attention_ragged_bf16(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(o2), D, D, D, D, _lib.ptr(cu_q),
+                                               total, max(qlens), kv, B, H, _stream()), "attn ragged mma")
+    lib.taste_attention_set_mode(0)
+    for b in range(B):
+        qs = int(cu_q[b])
+        qb = q[qs:qs + qlens[b]].float().view(-1, H, 64).transpose(0, 1)
+        kb = k[b * kv:(b + 1) * kv].float().view(-1, H, 64).transpose(0, 1)
+        vb = v[b * kv:(b + 1) * kv].float().view(-1, H, 64).transpose(0, 1)
+        ref = _attn_ref(qb, kb, vb, False).transpose(0, 1).reshape(qlens[b], D)
+        assert _rel(o[qs:qs + qlens[b]].float(), ref) < 6e-3, b
+        assert _rel(o2[qs:qs + qlens[b]].float(), ref) < 6e-3, b
 
 
 # ---------------------------------------------------------------------------------------------------------------
