@@ -126,7 +126,7 @@ typedef struct {
   /* RVQ (RVQ:102-170, VQ:266-340); all fp32 */
   const float* rvq_win_t;     /* [D][256]      project_in.weight transposed */
   const float* rvq_bin;       /* [256] */
-  const float* rvq_code_t;    /* [Q][256][512] codebooks transposed (distance pass) */
+  const void* rvq_code_split; /* bf16 [Q][2][512][256]: hi = bf16(e), lo = bf16(e - hi) planes of the codebooks (tensor-core distance pass) */
   const float* rvq_code;      /* [Q][512][256] codebooks (gather) */
   const float* rvq_code_sq;   /* [Q][512]      |e|^2 */
   const float* rvq_wout_t;    /* [256][D]      project_out.weight transposed */
@@ -186,9 +186,12 @@ int taste_word_pool_f32(const float* dec_out, const int32_t* cu_tokens, const in
 /* z fp32 [batch,tmax,in_dim]; lengths int32 [batch] (mask = t < lengths[b], modules_taste/utils.py:5-8; NULL =
  * all valid).  in_dim == d_model: project_in is applied (RVQ:371); in_dim == 256: `z` is already a code
  * (ResidualVQ.get_indices_from_code, RVQ:258-357).  indices int64 [batch,tmax,Q] (-1 at masked rows);
- * quantized fp32 [batch,tmax,D] (nullable) = project_out(sum of codes) (RVQ:470). */
+ * quantized fp32 [batch,tmax,D] (nullable) = project_out(sum of codes) (RVQ:470).
+ * ws: taste_rvq_ws_bytes(batch * tmax) bytes of device scratch (projected input and code sums; residuals themselves
+ * never leave the SM between levels). */
+size_t taste_rvq_ws_bytes(int n_rows);
 int taste_rvq_encode_f32(taste_handle_t h, const float* z, const int32_t* lengths, int batch, int tmax, int in_dim,
-                         int64_t* indices, float* quantized, void* stream);
+                         int64_t* indices, float* quantized, void* ws, size_t ws_bytes, void* stream);
 /* ResidualVQ.get_output_from_indices / get_code_from_indices (RVQ:183-242): indices int64 [n,Q] (-1 -> zero code).
  * out fp32 [n, D] if project_out != 0 else [n, 256]. */
 int taste_rvq_decode_f32(taste_handle_t h, const int64_t* indices, int n, int project_out, float* out, void* stream);

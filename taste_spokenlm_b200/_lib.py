@@ -54,7 +54,7 @@ class Weights(C.Structure):
         "dft_cos", "dft_sin", "hann", "mel_start", "mel_count", "mel_weight", "dft_w_bf16",
         "conv1_w", "conv1_b", "conv2_w", "conv2_b", "enc_pos", "enc", "enc_ln_w", "enc_ln_b",
         "tok_emb", "dec_pos", "dec", "dec_ln_w", "dec_ln_b",
-        "rvq_win_t", "rvq_bin", "rvq_code_t", "rvq_code", "rvq_code_sq", "rvq_wout_t", "rvq_bout")]
+        "rvq_win_t", "rvq_bin", "rvq_code_split", "rvq_code", "rvq_code_sq", "rvq_wout_t", "rvq_bout")]
 
 
 class ProfEntry(C.Structure):
@@ -78,7 +78,8 @@ _SIGS = {
     "taste_aggregator_fwd": (C.c_int, [p, p, p, p, p, C.c_int, C.c_int, C.c_int, p, p, C.c_size_t, p]),
     "taste_assemble_tokens": (C.c_int, [p, p, p, C.c_int, C.c_int, p, p]),
     "taste_word_pool_f32": (C.c_int, [p, p, p, p, C.c_int, C.c_int, C.c_int, p, p]),
-    "taste_rvq_encode_f32": (C.c_int, [p, p, p, C.c_int, C.c_int, C.c_int, p, p, p]),
+    "taste_rvq_ws_bytes": (C.c_size_t, [C.c_int]),
+    "taste_rvq_encode_f32": (C.c_int, [p, p, p, C.c_int, C.c_int, C.c_int, p, p, p, C.c_size_t, p]),
     "taste_rvq_decode_f32": (C.c_int, [p, p, C.c_int, C.c_int, p, p]),
     "taste_map_to_llm_tokens": (C.c_int, [p, p, p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, p, p]),
     "taste_resample_mean_f32": (C.c_int, [p, p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, p, p, C.c_int, C.c_int, C.c_int,

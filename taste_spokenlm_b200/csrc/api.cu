@@ -405,10 +405,13 @@ int taste_word_pool_f32(const float* dec_out, const int32_t* cu_tokens, const in
                           static_cast<cudaStream_t>(stream));
 }
 
+size_t taste_rvq_ws_bytes(int n_rows) { return rvq_ws_bytes(n_rows); }
+
 int taste_rvq_encode_f32(taste_handle_t h, const float* z, const int32_t* lengths, int batch, int tmax, int in_dim,
-                         int64_t* indices, float* quantized, void* stream) {
+                         int64_t* indices, float* quantized, void* ws, size_t ws_bytes, void* stream) {
   if (!h) return set_error(TASTE_E_ARG, "rvq_encode: null handle");
-  return launch_rvq_encode(h->w, z, lengths, batch, tmax, in_dim, indices, quantized, static_cast<cudaStream_t>(stream));
+  return launch_rvq_encode(h->w, z, lengths, batch, tmax, in_dim, indices, quantized, ws, ws_bytes,
+                           static_cast<cudaStream_t>(stream));
 }
 
 int taste_rvq_decode_f32(taste_handle_t h, const int64_t* indices, int n, int project_out, float* out, void* stream) {

@@ -32,7 +32,7 @@ int set_error(int code, const char* fmt, ...);
 enum KernelClass {
   KC_GEMM = 0, KC_ATTN_ENC, KC_ATTN_AGG, KC_LAYERNORM, KC_CAST, KC_LOGMEL_TILE, KC_LOGMEL_FINISH, KC_EMBED,
   KC_WORD_POOL, KC_RVQ_ENCODE, KC_RVQ_DECODE, KC_MAP_LLM, KC_ATTN_TC, KC_RESAMPLE, KC_LOGMEL_SPLIT, KC_LOGMEL_DFT,
-  KC_LOGMEL_MEL, KC_COUNT
+  KC_LOGMEL_MEL, KC_RVQ_PROJ, KC_COUNT
 };
 // Wrap a kernel launch: counts it and, when profiling is on, brackets it with CUDA events on `stream`.
 // flops / bytes are the ALGORITHMIC work of the launch (DESIGN.md "Kernels").
@@ -137,7 +137,8 @@ void set_logmel_mode(int mode);
 
 // ---- RVQ (rvq.cu) ----
 int launch_rvq_encode(const taste_weights_t& w, const float* z, const int32_t* lengths, int batch, int tmax, int in_dim,
-                      int64_t* indices, float* quantized, cudaStream_t stream);
+                      int64_t* indices, float* quantized, void* ws, size_t ws_bytes, cudaStream_t stream);
+size_t rvq_ws_bytes(int n_rows);
 int launch_rvq_decode(const taste_weights_t& w, const int64_t* indices, int n, bool project_out, float* out,
                       cudaStream_t stream);
 

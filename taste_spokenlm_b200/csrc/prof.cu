@@ -12,7 +12,7 @@ namespace taste {
 static const char* kClassNames[KC_COUNT] = {
     "gemm_bf16_tcgen05", "attention_encoder", "attention_aggregator", "layernorm", "cast_bf16", "logmel_tile",
     "logmel_finish",     "embed",             "word_pool",            "rvq_encode", "rvq_decode", "map_llm",
-    "attention_tcgen05", "resample_mean",     "logmel_split",         "logmel_dft", "logmel_mel",
+    "attention_tcgen05", "resample_mean",     "logmel_split",         "logmel_dft", "logmel_mel", "rvq_project",
 };
 
 struct ProfRecord {

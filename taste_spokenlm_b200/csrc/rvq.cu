@@ -1,190 +1,464 @@
-// Fused residual vector quantiser, fp32 (AQ:109-124 -> RVQ:359-490 -> VQ:955-1217 -> VQ:462-566; Appendix A6).
+// Residual vector quantiser (AQ:109-124 -> RVQ:359-490 -> VQ:955-1217 -> VQ:462-566; Appendix A6).
 //
-// One CTA owns 16 tokens end to end: project_in -> 4 x { distances to 512 codes, first-arg-min, gather,
-// residual -= code, acc += code } -> project_out.  Residuals and the running sum live in shared memory: nothing
-// round-trips HBM between levels.  Arithmetic is deliberately fp32 FFMA, not tensor cores: the contract is
-// bit-identical indices against the reference's fp32 path (SURVEY §0 finding 8), and the stage is <0.01 % of the
-// path's FLOPs.  The distance follows the reference's operation order exactly (VQ:44-48):
-//   d = sqrt(max((|r|^2 + |e|^2) + (-2 * <r,e>), 0)),  index = first minimum of d (argmax of -d, VQ:102).
+// Contract: indices bit-identical to the reference's fp32 formula (VQ:44-48, VQ:102)
+//     d_j = sqrt(max((|r|^2 + |e_j|^2) + (-2 <r, e_j>), 0)),   index = first minimum of d_j
+// given the same input.  Three kernels:
+//   1. rvq_sgemm_kernel      x = project_in(z)  (RVQ:371), fp32 FFMA: every output is one k-ascending fma chain
+//   2. rvq_search_kernel     128 tokens per CTA, all levels fused, residuals never leave the SM:
+//        * the 512 dot products <r, e_j> of a level run on the tensor cores (tcgen05.mma, fp32 accumulators in TMEM) as a
+//          split-bf16 three-product GEMM: r = r_hi + r_lo, e = e_hi + e_lo, <r,e> ~ r_hi.e_hi + r_hi.e_lo + r_lo.e_hi
+//          (worst-case error 1.1e-5 |r||e|); the codebook planes arrive by TMA through a 3-stage ring, the residual planes
+//          are written by the row threads straight into the 128-byte-swizzled K-major layout the MMA reads;
+//        * the fp32 residual of every token lives in TMEM (columns 256..511, one lane per token) next to the 256
+//          distance columns of the current half of the codebook;
+//        * one thread per token scans its distances with a fused arg-min that keeps every code whose lower error bound
+//          lies below the smallest upper bound (error bound 3e-5 (|r|^2 + |e_j|^2) per score).  A single survivor
+//          (99.7 % of the tokens) IS the fp32 arg-min; otherwise the survivors are re-evaluated with the exact fp32
+//          formula, operation order and first-minimum tie-break of the reference, so indices stay bit-exact;
+//        * gather, residual -= code, re-split into bf16 planes for the next level.
+//   3. rvq_sgemm_kernel      quantized = project_out(sum of codes)  (RVQ:470), fp32 FFMA as above
 #include "common.cuh"
 #include "internal.h"
 
 namespace taste {
 
-constexpr int RVQ_ROWS = 16;
+constexpr int RVQ_ROWS = 16;         // decode kernel: tokens per CTA
 constexpr int RVQ_THREADS = 256;
-constexpr int RVQ_DC = 256;      // codebook dim
-constexpr int RVQ_K = 512;       // codes per level
+constexpr int RVQ_DC = 256;          // codebook dim
+constexpr int RVQ_K = 512;           // codes per level
 constexpr int RVQ_MAXQ = 8;
 
-// x rows are staged in chunks of 256 input dims
-__global__ void __launch_bounds__(RVQ_THREADS)
-rvq_encode_kernel(const float* __restrict__ z, const int32_t* __restrict__ lengths, int tmax, int n_rows, int in_dim,
-                  int d_model, int n_q, const float* __restrict__ win_t, const float* __restrict__ bin,
-                  const float* __restrict__ code_t, const float* __restrict__ code, const float* __restrict__ code_sq,
-                  const float* __restrict__ wout_t, const float* __restrict__ bout, int64_t* __restrict__ indices,
-                  float* __restrict__ quantized) {
-  __shared__ __align__(16) float s_res[RVQ_ROWS][RVQ_DC];       // residual
-  __shared__ __align__(16) float s_acc[RVQ_ROWS][RVQ_DC];       // sum of selected codes
-  float (*s_in)[RVQ_DC] = s_acc;                  // input staging chunk; dead before s_acc is first used
-  __shared__ float s_x2[RVQ_ROWS];
-  __shared__ float s_bd[RVQ_THREADS / 32][RVQ_ROWS];
-  __shared__ int s_bi[RVQ_THREADS / 32][RVQ_ROWS];
-  __shared__ int s_idx[RVQ_ROWS];
-  __shared__ int s_valid[RVQ_ROWS];
-
+// ------------------------------------------------------------------------------------------------
+// fp32 projection GEMM: C[m, n] = bias[n] + sum_k A[m, k] * Bt[k, n]; each output is ONE fma chain over ascending k
+// (the reference is fp32; a tensor-core product would change the indices it feeds).  64 x 64 tile, 4 x 4 per thread.
+// ------------------------------------------------------------------------------------------------
+constexpr int SG_T = 64, SG_K = 16;
+__global__ void __launch_bounds__(256)
+rvq_sgemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bt, int ldb,
+                 const float* __restrict__ bias, float* __restrict__ C, int ldc, int M, int N, int K) {
+  __shared__ __align__(16) float sA[SG_K][SG_T + 4];      // [k][m]  (transposed on the way in)
+  __shared__ __align__(16) float sB[SG_K][SG_T];          // [k][n]
   const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
-  const int row0 = blockIdx.x * RVQ_ROWS;
-
-  if (tid < RVQ_ROWS) {
-    const int r = row0 + tid;
-    int ok = 0;
-    if (r < n_rows) {
-      const int b = r / tmax, t = r - b * tmax;
-      ok = lengths ? (t < lengths[b]) : 1;
+  const int tx = tid & 15, ty = tid >> 4;                 // 16 x 16 threads, 4 x 4 outputs each
+  const int m0 = blockIdx.y * SG_T, n0 = blockIdx.x * SG_T;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int a_row = tid >> 2, a_k4 = (tid & 3) * 4;       // A tile: 64 rows x 16 k, one float4 per thread
+  const int b_k = tid >> 4, b_n4 = (tid & 15) * 4;        // B tile: 16 k x 64 n, one float4 per thread
+  for (int k0 = 0; k0 < K; k0 += SG_K) {
+    float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m0 + a_row < M) av = *reinterpret_cast<const float4*>(A + int64_t(m0 + a_row) * lda + k0 + a_k4);
+    if (n0 + b_n4 < N) bv = __ldg(reinterpret_cast<const float4*>(Bt + int64_t(k0 + b_k) * ldb + n0 + b_n4));
+    __syncthreads();
+    sA[a_k4 + 0][a_row] = av.x;
+    sA[a_k4 + 1][a_row] = av.y;
+    sA[a_k4 + 2][a_row] = av.z;
+    sA[a_k4 + 3][a_row] = av.w;
+    *reinterpret_cast<float4*>(&sB[b_k][b_n4]) = bv;
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < SG_K; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&sA[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&sB[kk][tx * 4]);
+      const float ar[4] = {a.x, a.y, a.z, a.w}, br[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
     }
-    s_valid[tid] = ok;
   }
+  if (n0 + tx * 4 < N) {
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + n0 + tx * 4));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + ty * 4 + i;
+      if (m < M)
+        *reinterpret_cast<float4*>(C + int64_t(m) * ldc + n0 + tx * 4) =
+            make_float4(acc[i][0] + bb.x, acc[i][1] + bb.y, acc[i][2] + bb.z, acc[i][3] + bb.w);
+    }
+  }
+}
 
-  // ---- project_in (RVQ:371) or pass-through when the input is already a code (RVQ:258-357) ----
-  if (in_dim == RVQ_DC) {
-    for (int i = tid; i < RVQ_ROWS * RVQ_DC; i += RVQ_THREADS) {
-      const int r = i / RVQ_DC, c = i - r * RVQ_DC;
-      s_res[r][c] = (row0 + r < n_rows) ? z[int64_t(row0 + r) * in_dim + c] : 0.f;
+// ------------------------------------------------------------------------------------------------
+// the search: tcgen05 / TMEM / TMA
+// ------------------------------------------------------------------------------------------------
+constexpr int RS_ROWS = 128;                       // tokens per CTA = TMEM lanes
+constexpr int RS_THREADS = 192;                    // warps 0..3: one thread per token; warp 4: TMA; warp 5: MMA issuer
+constexpr int RS_STAGES = 3;
+constexpr uint32_t RS_A_ATOM = 128 * 128;          // [128 tokens x 64 dims] bf16, 128-byte rows, 8-row swizzle atoms
+constexpr uint32_t RS_A_PLANE = 4 * RS_A_ATOM;     // 256 dims
+constexpr uint32_t RS_B_TILE = 256 * 128;          // [256 codes x 64 dims] bf16
+constexpr size_t RS_SMEM = 1024 + 2 * RS_A_PLANE + RS_STAGES * RS_B_TILE + 128;
+constexpr uint32_t RS_COL_D = 0, RS_COL_R = 256;   // TMEM columns: distances of the current half / fp32 residual
+constexpr float RS_KAPPA = 3.0e-5f;                // |score error| <= RS_KAPPA * (|r|^2 + |e_j|^2)   (see header)
+constexpr int RS_CAND = 4;
+static_assert(RS_SMEM <= 232448, "shared memory");
+
+struct RsParams {
+  const float* x;            // [n_rows, ldx] fp32: project_in output (or the codes themselves, RVQ:258-357)
+  int ldx;
+  const int32_t* lengths;    // [batch] or null
+  int tmax, n_rows, n_q;
+  const float* code;         // [Q][512][256] fp32
+  const float* code_sq;      // [Q][512]
+  int64_t* indices;          // [n_rows, n_q]
+  float* code_sum;           // [n_rows, 256] fp32 or null: sum over levels of the selected codes (RVQ:455-456)
+};
+
+__global__ void __launch_bounds__(RS_THREADS, 1)
+rvq_search_kernel(const __grid_constant__ CUtensorMap tma_code, const RsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sAhi = smem;
+  uint8_t* sAlo = smem + RS_A_PLANE;
+  uint8_t* sB = smem + 2 * RS_A_PLANE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + size_t(RS_STAGES) * RS_B_TILE);
+  uint64_t* b_full = bars;                      // [RS_STAGES]
+  uint64_t* b_empty = bars + RS_STAGES;         // [RS_STAGES]
+  uint64_t* a_full = bars + 2 * RS_STAGES;      // residual planes of a level written   (rows -> MMA), 4 warp arrivals
+  uint64_t* d_full = a_full + 1;                // distances of a half complete          (MMA -> rows)
+  uint64_t* d_free = a_full + 2;                // distances of a half read              (rows -> MMA), 4 warp arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 3);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tma_code);
+    for (int s = 0; s < RS_STAGES; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    mbar_init(a_full, 4);
+    mbar_init(d_full, 1);
+    mbar_init(d_free, 4);
+    fence_barrier_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ===================== TMA producer: codebook planes, in the order the MMA warp consumes them =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int q = 0; q < p.n_q; ++q)
+      for (int half = 0; half < 2; ++half)
+        for (int kc = 0; kc < 4; ++kc)
+          for (int plane = 0; plane < 2; ++plane) {
+            mbar_wait_relaxed(&b_empty[stage], phase ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(&b_full[stage], RS_B_TILE);
+              tma_load_2d(sB + size_t(stage) * RS_B_TILE, &tma_code, &b_full[stage], kc * 64,
+                          (q * 2 + plane) * RVQ_K + half * 256);
+            }
+            __syncwarp();
+            if (++stage == RS_STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc(RS_ROWS, 256, /*bf16*/ 1, 0, 0);
+    const uint32_t d_tmem = tmem_base + RS_COL_D;
+    int stage = 0;
+    uint32_t phase = 0;
+    int g = 0;                                   // (level, half) counter
+    for (int q = 0; q < p.n_q; ++q) {
+      mbar_wait(a_full, uint32_t(q & 1));
+      tc_fence_after();
+      for (int half = 0; half < 2; ++half, ++g) {
+        if (g > 0) {
+          mbar_wait(d_free, uint32_t((g - 1) & 1));
+          tc_fence_after();
+        }
+        for (int kc = 0; kc < 4; ++kc)
+          for (int plane = 0; plane < 2; ++plane) {
+            mbar_wait(&b_full[stage], phase);
+            tc_fence_after();
+            const uint64_t db = umma_desc_k_sw128(smem_u32(sB + size_t(stage) * RS_B_TILE));
+            const uint64_t da_hi = umma_desc_k_sw128(smem_u32(sAhi + size_t(kc) * RS_A_ATOM));
+            const uint64_t da_lo = umma_desc_k_sw128(smem_u32(sAlo + size_t(kc) * RS_A_ATOM));
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)          // r_hi . e_{hi|lo}
+                umma_ss(d_tmem, da_hi + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kc | plane | k) != 0 ? 1u : 0u);
+              if (plane == 0) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)        // r_lo . e_hi
+                  umma_ss(d_tmem, da_lo + uint64_t(k * 2), db + uint64_t(k * 2), idesc, 1u);
+              }
+              umma_commit(&b_empty[stage]);
+              if (kc == 3 && plane == 1) umma_commit(d_full);
+            }
+            __syncwarp();
+            if (++stage == RS_STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+      }
     }
   } else {
-    float acc[RVQ_ROWS];
-#pragma unroll
-    for (int r = 0; r < RVQ_ROWS; ++r) acc[r] = 0.f;
-    for (int k0 = 0; k0 < in_dim; k0 += RVQ_DC) {
-      __syncthreads();
-      for (int i = tid; i < RVQ_ROWS * RVQ_DC; i += RVQ_THREADS) {
-        const int r = i / RVQ_DC, c = i - r * RVQ_DC;
-        s_in[r][c] = (row0 + r < n_rows && k0 + c < in_dim) ? z[int64_t(row0 + r) * in_dim + k0 + c] : 0.f;
-      }
-      __syncthreads();
-      // four k at a time: one 16-byte broadcast read of the staged row per 4 multiply-adds (the loop is LDS-bound)
-      const int kmax = min(RVQ_DC, in_dim - k0);           // in_dim is a multiple of 4 (checked by the launcher)
-#pragma unroll 2
-      for (int k = 0; k < kmax; k += 4) {
-        const float w0 = __ldg(win_t + int64_t(k0 + k + 0) * RVQ_DC + tid);
-        const float w1 = __ldg(win_t + int64_t(k0 + k + 1) * RVQ_DC + tid);
-        const float w2 = __ldg(win_t + int64_t(k0 + k + 2) * RVQ_DC + tid);
-        const float w3 = __ldg(win_t + int64_t(k0 + k + 3) * RVQ_DC + tid);
-#pragma unroll
-        for (int r = 0; r < RVQ_ROWS; ++r) {
-          const float4 x = *reinterpret_cast<const float4*>(&s_in[r][k]);
-          acc[r] = fmaf(x.w, w3, fmaf(x.z, w2, fmaf(x.y, w1, fmaf(x.x, w0, acc[r]))));
-        }
-      }
+    // ===================== one thread per token =====================
+    const int row_in = warp * 32 + lane;
+    const int row = blockIdx.x * RS_ROWS + row_in;
+    const bool in_range = row < p.n_rows;
+    bool valid = in_range;
+    if (in_range && p.lengths) {
+      const int b = row / p.tmax;
+      valid = (row - b * p.tmax) < __ldg(p.lengths + b);
     }
-    const float bv = __ldg(bin + tid);
-#pragma unroll
-    for (int r = 0; r < RVQ_ROWS; ++r) s_res[r][tid] = acc[r] + bv;
-  }
-  __syncthreads();       // all reads of the staging chunk (aliases s_acc) are done
-#pragma unroll
-  for (int r = 0; r < RVQ_ROWS; ++r) s_acc[r][tid] = 0.f;
-  __syncthreads();
-
-  for (int q = 0; q < n_q; ++q) {
-    // |r|^2 per row: warp w handles rows 2w, 2w+1
-    for (int r = warp * 2; r < warp * 2 + 2; ++r) {
-      float p = 0.f;
-      for (int c = lane; c < RVQ_DC; c += 32) p = fmaf(s_res[r][c], s_res[r][c], p);
-      p = warp_sum(p);
-      if (lane == 0) s_x2[r] = p;
-    }
-    // <r, e_j> for codes j = tid and tid + 256
-    float d0[RVQ_ROWS], d1[RVQ_ROWS];
-#pragma unroll
-    for (int r = 0; r < RVQ_ROWS; ++r) d0[r] = d1[r] = 0.f;
-    const float* ct = code_t + int64_t(q) * RVQ_DC * RVQ_K;
-#pragma unroll 1
-    for (int c = 0; c < RVQ_DC; c += 4) {
-      float e0[4], e1[4];
+    const uint32_t lane_base = tmem_base + (uint32_t(warp * 32) << 16);
+    const uint32_t t_d = lane_base + RS_COL_D, t_r = lane_base + RS_COL_R;
+    float x2p[32];                                  // |r|^2 partial sums, combined like the fp32 kernel's warp reduction
+    // bf16 split of 32 residual values -> the swizzled K-major planes (chunk c of the row: dims 32 c .. 32 c + 31)
+    auto write_planes = [&](int c, const float (&v)[32]) {
+      uint8_t* hi = sAhi + size_t(c >> 1) * RS_A_ATOM + size_t(row_in) * 128;
+      uint8_t* lo = sAlo + size_t(c >> 1) * RS_A_ATOM + size_t(row_in) * 128;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        e0[u] = __ldg(ct + (c + u) * RVQ_K + tid);
-        e1[u] = __ldg(ct + (c + u) * RVQ_K + tid + RVQ_THREADS);
-      }
+        uint4 h, l;
+        uint32_t hw[4], lw[4];
 #pragma unroll
-      for (int r = 0; r < RVQ_ROWS; ++r) {
-        const float4 rv = *reinterpret_cast<const float4*>(&s_res[r][c]);
-        // same summation order as one element at a time (c ascending), so the distances are bit-identical
-        d0[r] = fmaf(rv.w, e0[3], fmaf(rv.z, e0[2], fmaf(rv.y, e0[1], fmaf(rv.x, e0[0], d0[r]))));
-        d1[r] = fmaf(rv.w, e1[3], fmaf(rv.z, e1[2], fmaf(rv.y, e1[1], fmaf(rv.x, e1[0], d1[r]))));
+        for (int e = 0; e < 4; ++e) {
+          const float a = v[8 * u + 2 * e], b = v[8 * u + 2 * e + 1];
+          const float ah = __bfloat162float(__float2bfloat16_rn(a)), bh = __bfloat162float(__float2bfloat16_rn(b));
+          hw[e] = pack_true_bf16x2(ah, bh);
+          lw[e] = pack_true_bf16x2(a - ah, b - bh);
+        }
+        h = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        l = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        const int chunk = ((c & 1) * 4 + u) ^ (row_in & 7);
+        *reinterpret_cast<uint4*>(hi + chunk * 16) = h;
+        *reinterpret_cast<uint4*>(lo + chunk * 16) = l;
       }
-    }
-    __syncthreads();     // s_x2 visible
-    const float y0 = __ldg(code_sq + q * RVQ_K + tid);
-    const float y1 = __ldg(code_sq + q * RVQ_K + tid + RVQ_THREADS);
+    };
+    auto x2_total = [&]() {                          // the butterfly of warp_sum on 32 lane-strided partials
+      float a[16], b[8], c4[4];
 #pragma unroll
-    for (int r = 0; r < RVQ_ROWS; ++r) {
-      const float x2 = s_x2[r];
-      const float s0 = __fadd_rn(__fadd_rn(x2, y0), __fmul_rn(d0[r], -2.0f));
-      const float s1 = __fadd_rn(__fadd_rn(x2, y1), __fmul_rn(d1[r], -2.0f));
-      float bd = __fsqrt_rn(fmaxf(s0, 0.f));
-      int bi = tid;
-      const float dd1 = __fsqrt_rn(fmaxf(s1, 0.f));
-      if (dd1 < bd) { bd = dd1; bi = tid + RVQ_THREADS; }
-      // warp arg-min, ties -> smaller index (first maximum of -d)
+      for (int l = 0; l < 16; ++l) a[l] = x2p[l] + x2p[l + 16];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float od = __shfl_xor_sync(0xffffffffu, bd, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
-      }
-      if (lane == 0) { s_bd[warp][r] = bd; s_bi[warp][r] = bi; }
-    }
-    __syncthreads();
-    if (tid < RVQ_ROWS) {
-      float bd = s_bd[0][tid];
-      int bi = s_bi[0][tid];
-      for (int w = 1; w < RVQ_THREADS / 32; ++w) {
-        const float od = s_bd[w][tid];
-        const int oi = s_bi[w][tid];
-        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
-      }
-      s_idx[tid] = bi;
-      const int r = row0 + tid;
-      if (r < n_rows) indices[int64_t(r) * n_q + q] = s_valid[tid] ? int64_t(bi) : int64_t(-1);   // VQ:1205-1210
-    }
-    __syncthreads();
-    // gather + residual update; masked rows contribute a zero code (VQ:1192-1203, RVQ:455-456)
-    const float* cb = code + int64_t(q) * RVQ_K * RVQ_DC;
+      for (int l = 0; l < 8; ++l) b[l] = a[l] + a[l + 8];
 #pragma unroll
-    for (int r = 0; r < RVQ_ROWS; ++r) {
-      if (s_valid[r]) {
-        const float cv = __ldg(cb + int64_t(s_idx[r]) * RVQ_DC + tid);
-        s_res[r][tid] = s_res[r][tid] - cv;
-        s_acc[r][tid] = s_acc[r][tid] + cv;
+      for (int l = 0; l < 4; ++l) c4[l] = b[l] + b[l + 4];
+      return (c4[0] + c4[2]) + (c4[1] + c4[3]);
+    };
+    // ---- level 0 residual = x ----
+#pragma unroll
+    for (int l = 0; l < 32; ++l) x2p[l] = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      float v[32];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (in_range) t = *reinterpret_cast<const float4*>(p.x + int64_t(row) * p.ldx + c * 32 + u * 4);
+        v[4 * u + 0] = t.x; v[4 * u + 1] = t.y; v[4 * u + 2] = t.z; v[4 * u + 3] = t.w;
       }
+      uint32_t w[32];
+#pragma unroll
+      for (int l = 0; l < 32; ++l) {
+        w[l] = __float_as_uint(v[l]);
+        x2p[l] = fmaf(v[l], v[l], x2p[l]);
+      }
+      tmem_st_32x32b_x32(t_r + uint32_t(c * 32), w);
+      write_planes(c, v);
     }
-    __syncthreads();
-  }
+    tmem_st_wait();
+    fence_proxy_async();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(a_full);
 
-  // ---- project_out (RVQ:470) ----
-  if (quantized != nullptr) {
-    for (int c0 = 0; c0 < d_model; c0 += RVQ_THREADS) {
-      const int col = c0 + tid;
-      if (col >= d_model) break;
-      float acc[RVQ_ROWS];
+    int chosen[RVQ_MAXQ];
+    int g = 0;
+#pragma unroll 1
+    for (int q = 0; q < p.n_q; ++q) {
+      const float x2 = x2_total();
+      const float kx2 = RS_KAPPA * x2;
+      const float* e2 = p.code_sq + q * RVQ_K;
+      float m_up = INFINITY;                        // smallest upper bound of a score seen so far
+      float cs[RS_CAND];                            // survivors: lower bound <= m_up when they were seen
+      int cj[RS_CAND];
+      int cnt = 0;
+      bool overflow = false;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half, ++g) {
+        mbar_wait(d_full, uint32_t(g & 1));
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          uint32_t dv[32];
+          __syncwarp();                              // the candidate branch below diverges; tcgen05.ld is warp-collective
+          tmem_ld_32x32b_x32(t_d + uint32_t(c * 32), dv);
+          tmem_ld_wait();
+          const int j0 = half * 256 + c * 32;
 #pragma unroll
-      for (int r = 0; r < RVQ_ROWS; ++r) acc[r] = 0.f;
-#pragma unroll 4
-      for (int k = 0; k < RVQ_DC; ++k) {
-        const float wv = __ldg(wout_t + int64_t(k) * d_model + col);
+          for (int u = 0; u < 8; ++u) {
+            const float4 y = __ldg(reinterpret_cast<const float4*>(e2 + j0 + 4 * u));
+            const float yy[4] = {y.x, y.y, y.z, y.w};
 #pragma unroll
-        for (int r = 0; r < RVQ_ROWS; ++r) acc[r] = fmaf(s_acc[r][k], wv, acc[r]);
+            for (int e = 0; e < 4; ++e) {
+              const float s = fmaf(-2.0f, __uint_as_float(dv[4 * u + e]), yy[e]);      // |e|^2 - 2 <r,e>  (+ |r|^2)
+              const float err = fmaf(RS_KAPPA, yy[e], kx2);
+              if (s - err <= m_up) {                 // rare after the first few codes
+                m_up = fminf(m_up, s + err);
+                const int j = j0 + 4 * u + e;
+                if (cnt < RS_CAND) {
+#pragma unroll
+                  for (int t = 0; t < RS_CAND; ++t)
+                    if (t == cnt) { cs[t] = s - err; cj[t] = j; }
+                  ++cnt;
+                } else {
+                  // keep the list short: drop entries the tighter bound has ruled out, then retry
+                  int n = 0;
+#pragma unroll
+                  for (int t = 0; t < RS_CAND; ++t)
+                    if (cs[t] <= m_up) {
+#pragma unroll
+                      for (int t2 = 0; t2 < RS_CAND; ++t2)
+                        if (t2 == n) { cs[t2] = cs[t]; cj[t2] = cj[t]; }
+                      ++n;
+                    }
+                  cnt = n;
+                  if (cnt < RS_CAND) {
+#pragma unroll
+                    for (int t = 0; t < RS_CAND; ++t)
+                      if (t == cnt) { cs[t] = s - err; cj[t] = j; }
+                    ++cnt;
+                  } else {
+                    overflow = true;
+                  }
+                }
+              }
+            }
+          }
+        }
+        __syncwarp();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d_free);
       }
-      const float bv = __ldg(bout + col);
+      // ---- decide ----
+      int n_live = 0, best = 0;
 #pragma unroll
-      for (int r = 0; r < RVQ_ROWS; ++r)
-        if (row0 + r < n_rows) quantized[int64_t(row0 + r) * d_model + col] = acc[r] + bv;
+      for (int t = 0; t < RS_CAND; ++t)
+        if (t < cnt && cs[t] <= m_up) {
+          ++n_live;
+          best = cj[t];
+        }
+      // exact fp32 re-evaluation (VQ:44-48 operation order, first minimum) of the survivors - of every code when a list
+      // overflowed.  tcgen05.ld is warp-collective, so the loop is warp-uniform and lanes that need nothing ride along.
+      const bool need = valid && (overflow || n_live > 1);
+      if (__any_sync(0xffffffffu, need)) {
+        const float* cb = p.code + int64_t(q) * RVQ_K * RVQ_DC;
+        const int n_try = __any_sync(0xffffffffu, need && overflow) ? RVQ_K : RS_CAND;
+        float bd = INFINITY;
+        int bi = 0;
+#pragma unroll 1
+        for (int t = 0; t < n_try; ++t) {
+          int j = t;
+          bool act = need;
+          if (!overflow) {
+            float lo_b = INFINITY;
+            j = 0;
+#pragma unroll
+            for (int t2 = 0; t2 < RS_CAND; ++t2)
+              if (t2 == t && t2 < cnt) { j = cj[t2]; lo_b = cs[t2]; }
+            act = need && lo_b <= m_up;
+          }
+          float dot = 0.f;
+#pragma unroll 1
+          for (int c = 0; c < 8; ++c) {
+            uint32_t rv[32];
+            tmem_ld_32x32b_x32(t_r + uint32_t(c * 32), rv);
+            tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float4 ev = __ldg(reinterpret_cast<const float4*>(cb + int64_t(j) * RVQ_DC + c * 32 + 4 * u));
+              dot = fmaf(__uint_as_float(rv[4 * u + 3]), ev.w,
+                         fmaf(__uint_as_float(rv[4 * u + 2]), ev.z,
+                              fmaf(__uint_as_float(rv[4 * u + 1]), ev.y, fmaf(__uint_as_float(rv[4 * u + 0]), ev.x, dot))));
+            }
+          }
+          const float sx = __fadd_rn(__fadd_rn(x2, __ldg(e2 + j)), __fmul_rn(dot, -2.0f));
+          const float dj = __fsqrt_rn(fmaxf(sx, 0.f));
+          if (act && (dj < bd || (dj == bd && j < bi))) {
+            bd = dj;
+            bi = j;
+          }
+        }
+        if (need) best = bi;
+      }
+      chosen[q] = best;
+      __syncwarp();
+      if (in_range) p.indices[int64_t(row) * p.n_q + q] = valid ? int64_t(best) : int64_t(-1);          // VQ:1205-1210
+      // ---- gather, residual -= code (masked rows: zero code, VQ:1192-1203), planes of the next level ----
+      if (q + 1 < p.n_q) {
+        const float* cv = p.code + (int64_t(q) * RVQ_K + best) * RVQ_DC;
+#pragma unroll
+        for (int l = 0; l < 32; ++l) x2p[l] = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          uint32_t rv[32];
+          tmem_ld_32x32b_x32(t_r + uint32_t(c * 32), rv);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            float4 ev = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) ev = __ldg(reinterpret_cast<const float4*>(cv + c * 32 + 4 * u));
+            v[4 * u + 0] = __uint_as_float(rv[4 * u + 0]) - ev.x;
+            v[4 * u + 1] = __uint_as_float(rv[4 * u + 1]) - ev.y;
+            v[4 * u + 2] = __uint_as_float(rv[4 * u + 2]) - ev.z;
+            v[4 * u + 3] = __uint_as_float(rv[4 * u + 3]) - ev.w;
+          }
+#pragma unroll
+          for (int l = 0; l < 32; ++l) {
+            rv[l] = __float_as_uint(v[l]);
+            x2p[l] = fmaf(v[l], v[l], x2p[l]);
+          }
+          tmem_st_32x32b_x32(t_r + uint32_t(c * 32), rv);
+          write_planes(c, v);
+        }
+        tmem_st_wait();
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full);
+      }
+    }
+    // ---- sum of the selected codes, level order (RVQ:455-456): the input of project_out ----
+    if (p.code_sum && in_range) {
+      float* dst = p.code_sum + int64_t(row) * RVQ_DC;
+#pragma unroll 1
+      for (int c4 = 0; c4 < RVQ_DC / 4; ++c4) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+          for (int q = 0; q < p.n_q; ++q) {
+            int j = 0;
+#pragma unroll
+            for (int t = 0; t < RVQ_MAXQ; ++t)
+              if (t == q) j = chosen[t];
+            const float4 ev = __ldg(reinterpret_cast<const float4*>(p.code + (int64_t(q) * RVQ_K + j) * RVQ_DC) + c4);
+            a.x += ev.x; a.y += ev.y; a.z += ev.z; a.w += ev.w;
+          }
+        }
+        reinterpret_cast<float4*>(dst)[c4] = a;
+      }
     }
   }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, 512);
 }
 
 // get_output_from_indices / get_code_from_indices (RVQ:183-242): one CTA per 16 rows.
@@ -236,28 +510,86 @@ static int check_rvq(const taste_weights_t& w) {
   if (w.dims.codebook_dim != RVQ_DC || w.dims.codebook_size != RVQ_K || w.dims.num_quantizers > RVQ_MAXQ ||
       w.dims.num_quantizers < 1)
     return set_error(TASTE_E_SHAPE, "rvq: kernel is built for codebook_dim 256, codebook_size 512, <= 8 levels");
-  if (!w.rvq_win_t || !w.rvq_bin || !w.rvq_code_t || !w.rvq_code || !w.rvq_code_sq || !w.rvq_wout_t || !w.rvq_bout)
+  if (!w.rvq_win_t || !w.rvq_bin || !w.rvq_code || !w.rvq_code_sq || !w.rvq_wout_t || !w.rvq_bout)
     return set_error(TASTE_E_ARG, "rvq: weights missing from the handle");
   return 0;
 }
 
+size_t rvq_ws_bytes(int n_rows) { return size_t(n_rows > 0 ? n_rows : 0) * RVQ_DC * sizeof(float) * 2 + 256; }
+
+static int launch_sgemm(const float* A, int lda, const float* Bt, int ldb, const float* bias, float* C, int ldc, int M,
+                        int N, int K, cudaStream_t stream) {
+  if (K % SG_K != 0 || N % 4 != 0 || lda % 4 != 0 || ldb % 4 != 0 || ldc % 4 != 0)
+    return set_error(TASTE_E_SHAPE, "rvq projection: K must be a multiple of 16 and N / strides multiples of 4");
+  dim3 grid((N + SG_T - 1) / SG_T, (M + SG_T - 1) / SG_T);
+  ProfScope ps(stream, KC_RVQ_PROJ, 2.0 * M * double(N) * K, 4.0 * (double(M) * K + double(K) * N + double(M) * N));
+  rvq_sgemm_kernel<<<grid, 256, 0, stream>>>(A, lda, Bt, ldb, bias, C, ldc, M, N, K);
+  TASTE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int launch_rvq_encode(const taste_weights_t& w, const float* z, const int32_t* lengths, int batch, int tmax, int in_dim,
-                      int64_t* indices, float* quantized, cudaStream_t stream) {
+                      int64_t* indices, float* quantized, void* ws, size_t ws_bytes, cudaStream_t stream) {
   if (int rc = check_rvq(w)) return rc;
   if (!z || !indices) return set_error(TASTE_E_ARG, "rvq_encode: null pointer");
+  if (!w.rvq_code_split) return set_error(TASTE_E_ARG, "rvq_encode: split codebook planes missing from the handle");
   if (in_dim != w.dims.d_model && in_dim != RVQ_DC) return set_error(TASTE_E_SHAPE, "rvq_encode: in_dim must be d_model or 256");
   const int n_rows = batch * tmax;
   if (n_rows <= 0) return 0;
-  const int blocks = (n_rows + RVQ_ROWS - 1) / RVQ_ROWS;
-  const double per_row = (in_dim == RVQ_DC ? 0.0 : 2.0 * in_dim * RVQ_DC) + w.dims.num_quantizers * 2.0 * RVQ_DC * RVQ_K +
-                         (quantized ? 2.0 * RVQ_DC * w.dims.d_model : 0.0);
-  ProfScope ps(stream, KC_RVQ_ENCODE, per_row * n_rows,
-               double(n_rows) * (4.0 * in_dim + 8.0 * w.dims.num_quantizers + (quantized ? 4.0 * w.dims.d_model : 0.0)));
-  rvq_encode_kernel<<<blocks, RVQ_THREADS, 0, stream>>>(z, lengths, tmax, n_rows, in_dim, w.dims.d_model,
-                                                        w.dims.num_quantizers, w.rvq_win_t, w.rvq_bin, w.rvq_code_t,
-                                                        w.rvq_code, w.rvq_code_sq, w.rvq_wout_t, w.rvq_bout, indices,
-                                                        quantized);
-  TASTE_CUDA_OK(cudaGetLastError());
+  if (!ws || ws_bytes < rvq_ws_bytes(n_rows))
+    return set_error(TASTE_E_WORKSPACE, "rvq_encode: workspace %zu < %zu", ws_bytes, rvq_ws_bytes(n_rows));
+  float* x = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
+  float* code_sum = x + size_t(n_rows) * RVQ_DC;
+  const int n_q = w.dims.num_quantizers;
+  int rc;
+  const float* x_in = z;
+  int ldx = in_dim;
+  if (in_dim != RVQ_DC) {                                                                               // RVQ:371
+    if ((rc = launch_sgemm(z, in_dim, w.rvq_win_t, RVQ_DC, w.rvq_bin, x, RVQ_DC, n_rows, RVQ_DC, in_dim, stream))) return rc;
+    x_in = x;
+    ldx = RVQ_DC;
+  }
+  EncodeTiledFn enc = get_tensor_map_encoder();
+  if (!enc) return set_error(TASTE_E_NO_DEVICE, "cuTensorMapEncodeTiled entry point unavailable");
+  CUtensorMap tm;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)RVQ_DC, (cuuint64_t)n_q * 2 * RVQ_K};
+    cuuint64_t strides[1] = {(cuuint64_t)RVQ_DC * 2};
+    cuuint32_t box[2] = {64, 256};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w.rvq_code_split), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error((int)r, "rvq: tensor map encode failed (%d)", (int)r);
+  }
+  static bool configured_dev[kMaxDevices] = {};
+  bool& configured = configured_dev[current_device()];
+  if (!configured) {
+    TASTE_CUDA_OK(cudaFuncSetAttribute(rvq_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM));
+    configured = true;
+  }
+  RsParams p;
+  p.x = x_in;
+  p.ldx = ldx;
+  p.lengths = lengths;
+  p.tmax = tmax;
+  p.n_rows = n_rows;
+  p.n_q = n_q;
+  p.code = w.rvq_code;
+  p.code_sq = w.rvq_code_sq;
+  p.indices = indices;
+  p.code_sum = quantized ? code_sum : nullptr;
+  {
+    // algorithmic work: the three bf16 products of every distance GEMM; bytes: residual in, indices (+ code sums) out
+    ProfScope ps(stream, KC_RVQ_ENCODE, 3.0 * 2.0 * RVQ_DC * RVQ_K * double(n_q) * n_rows,
+                 double(n_rows) * (4.0 * RVQ_DC + 8.0 * n_q + (quantized ? 4.0 * RVQ_DC : 0.0)));
+    rvq_search_kernel<<<(n_rows + RS_ROWS - 1) / RS_ROWS, RS_THREADS, RS_SMEM, stream>>>(tm, p);
+    TASTE_CUDA_OK(cudaGetLastError());
+  }
+  if (quantized)                                                                                         // RVQ:470
+    if ((rc = launch_sgemm(code_sum, RVQ_DC, w.rvq_wout_t, w.dims.d_model, w.rvq_bout, quantized, w.dims.d_model, n_rows,
+                           w.dims.d_model, RVQ_DC, stream)))
+      return rc;
   return 0;
 }
 

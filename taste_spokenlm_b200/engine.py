@@ -258,7 +258,10 @@ class TowerEngine(FrontendEngine):
         Q = cfg.num_quantizers
         embed = torch.stack([sd[f"{RVQ}layers.{q}._codebook.embed"].detach().float().cpu()[0] for q in range(Q)])  # [Q,K,dc]
         w.rvq_code = self._dev("rvq_code", embed.to(dev))
-        w.rvq_code_t = self._dev("rvq_code_t", embed.transpose(1, 2).contiguous().to(dev))
+        # split-bf16 planes for the tensor-core distance pass: e = hi + lo, [Q, 2, K, dc]
+        hi = embed.to(torch.bfloat16)
+        lo = (embed - hi.float()).to(torch.bfloat16)
+        w.rvq_code_split = self._dev("rvq_code_split", torch.stack([hi, lo], dim=1).contiguous().to(dev))
         # |e|^2 with the reference's own reduction (VQ:46) on the host, so the bits match the fp32 reference
         w.rvq_code_sq = self._dev("rvq_code_sq", (embed ** 2).sum(-1).to(dev))
         w.rvq_win_t = self._dev("rvq_win_t", sd[RVQ + "project_in.weight"].detach().float().t().contiguous().to(dev))
@@ -332,8 +335,12 @@ class TowerEngine(FrontendEngine):
         B, T, in_dim = z.shape
         idx = torch.empty(B, T, self.cfg.num_quantizers, dtype=torch.int64, device=z.device)
         qz = torch.empty(B, T, self.cfg.d_model, dtype=torch.float32, device=z.device) if want_quantized else None
+        if not hasattr(self, "_rvq_ws"):
+            self._rvq_ws = _Workspace(self.device)
+        ws = self._rvq_ws.get(self.lib.taste_rvq_ws_bytes(B * T))
         self._ck(self.lib.taste_rvq_encode_f32(self.handle, _lib.ptr(z), _lib.ptr(lengths), B, T, in_dim,
-                                                 _lib.ptr(idx), _lib.ptr(qz), self._stream()), "taste_rvq_encode_f32")
+                                                 _lib.ptr(idx), _lib.ptr(qz), _lib.ptr(ws), ws.numel(), self._stream()),
+                 "taste_rvq_encode_f32")
         return qz, idx
 
     @_on_device
