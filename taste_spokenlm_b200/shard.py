@@ -87,14 +87,17 @@ def gather_indices(hdr: torch.Tensor, flat: torch.Tensor, num_q: int, device=Non
 
 
 def _unpack(parts) -> List[Tuple[int, torch.Tensor]]:
-    out = []
-    for hdr, flat in parts:
-        off = 0
-        for u, t in hdr.tolist():
-            out.append((int(u), flat[off: off + t]))
-            off += t
-    out.sort(key=lambda x: x[0])
-    return out
+    """[(header [n, 2], flat [rows, Q])] per rank -> [(utterance id, [T, Q])] sorted by id (views of one tensor; no
+    per-row copies: with 16 k utterances per job a Python-level slice loop was most of the gather's wall time)."""
+    parts = [(h, f) for h, f in parts if h.shape[0] > 0]
+    if not parts:
+        return []
+    hdr = torch.cat([h for h, _ in parts])
+    flat = torch.cat([f for _, f in parts])
+    ids = hdr[:, 0].tolist()
+    pieces = torch.split(flat, hdr[:, 1].tolist())
+    order = sorted(range(len(ids)), key=ids.__getitem__)
+    return [(ids[i], pieces[i]) for i in order]
 
 
 class _Slot:

@@ -409,6 +409,35 @@ def test_rvq_random_vs_oracle(lib, rvq_engine):
     assert torch.allclose(qz.cpu()[3], W["vq.rvq.project_out.bias"].expand(33, -1))     # fully padded row
 
 
+@pytest.mark.parametrize("scale,rows", [(1.0, 4096), (13.0, 1500), (0.02, 700)])
+def test_rvq_search_survivor_paths_vs_oracle(lib, rvq_engine, scale, rows):
+    """The tensor-core search keeps every code whose error-bounded score could be the minimum; one survivor is the answer,
+    two are re-evaluated exactly by the token's thread, three or more by the whole warp.  |r| >> |e| (scale 13) widens the
+    bound relative to the score spacing and drives hundreds of tokens through both exact paths; |r| << |e| (scale 0.02)
+    makes the codes' own norms decide.  Indices must equal the fp32 oracle except fp64-verified ties."""
+    eng, W = rvq_engine
+    g = torch.Generator().manual_seed(int(scale * 100) + rows)
+    code = torch.randn(1, rows, 256, generator=g) * scale               # get_indices_from_code path: the search alone
+    _, idx = eng.rvq_encode(code.cuda(), None, want_quantized=False)
+    _, ridx = O.rvq_encode(W, code, None, project_in=False)
+    idx = idx.cpu()
+    bad = (idx != ridx).any(-1).nonzero()
+    for b, t in bad.tolist():
+        ql = int((idx[b, t] != ridx[b, t]).nonzero()[0])
+        assert _near_tie(W, code[b, t], ridx[b, t], idx[b, t], ql), (scale, t, idx[b, t], ridx[b, t])
+    assert len(bad) <= max(2, rows // 500), len(bad)
+    # with project_in / project_out around it
+    z = torch.randn(3, 40, 1280, generator=g) * scale
+    lens = torch.tensor([40, 7, 23], dtype=torch.int32)
+    mask = torch.arange(40)[None] < lens[:, None]
+    qz, idx2 = eng.rvq_encode(z.cuda(), lens.cuda())
+    rq, ridx2 = O.rvq_encode(W, z, mask)
+    assert torch.equal(idx2.cpu() < 0, ridx2 < 0)
+    same = (idx2.cpu() == ridx2).all(-1)
+    assert same.float().mean() > 0.97
+    assert _rel(qz.cpu()[same], rq[same]) < 1e-5
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # word pooling (JES:418-458 incl. the padded-row quirk) and the llm-token mapping
 # ---------------------------------------------------------------------------------------------------------------
