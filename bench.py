@@ -261,9 +261,21 @@ def measure_config5(tower, fe, batch, dev, args):
             torch.cuda.synchronize()
             return (time.perf_counter() - t0) * 1e3 / n
 
+        def generate_kv_cached():                     # taste_spokenlm_b200/generate.py: prompt once, then one position per step
+            out = lm.model(inputs_embeds=emb[:, :L], use_cache=True)
+            past = out.past_key_values
+            lm.lm_head(out.last_hidden_state[:, -1:])
+            for k in range(1, new_tokens):
+                out = lm.model(inputs_embeds=emb[:, L + k - 1: L + k], past_key_values=past, use_cache=True)
+                past = out.past_key_values
+                lm.lm_head(out.last_hidden_state[:, -1:])
+
         pre_ms = timed(prefill, 5)
         gen_ms = timed(generate_like_reference, 2)
+        gen_kv_ms = timed(generate_kv_cached, 2)
         res.update({"lm_prefill_ms": pre_ms, "lm_generate_ms": gen_ms, "lm_new_tokens": new_tokens,
+                    "lm_generate_kv_cached_ms": gen_kv_ms,
+                    "tokenizer_share_of_completion_kv_cached": tok_ms / (tok_ms + gen_kv_ms),
                     "lm": "HF transformers LlamaForCausalLM, random-init Llama-3.2-1B geometry (taslm.json text_config), bf16, "
                           "no KV cache as MT:1111-1117; measured in this run on the same GPU; bridge / sampler / speech "
                           "decoder excluded",

@@ -448,13 +448,19 @@ def extract_vq(model, asr_token_ids, asr_token_lengths, asr_word_ids, llm_token_
     return asr_indices, llm_indices
 
 
-def install(patch_frontend: bool = True, patch_extract_vq: bool = True) -> None:
-    """Swap the reference's classes for the B200 ones (needs `taste_speech` importable).  See INTEGRATION.md."""
+def install(patch_frontend: bool = True, patch_extract_vq: bool = True, patch_generate: bool = False) -> None:
+    """Swap the reference's classes for the B200 ones (needs `taste_speech` importable).  See INTEGRATION.md.
+
+    `patch_generate=True` additionally binds the KV-cached `generate.generate_kv_cached` as `TasteSpokenLM.generate`
+    (off by default: it is outside the tokenizer)."""
     import importlib
     mt = importlib.import_module("taste_speech.modeling_taste")
     mt.TasteAudioTower = TasteAudioTowerB200
     if patch_extract_vq and hasattr(mt, "TasteForCausalLM"):
         mt.TasteForCausalLM.extract_vq = extract_vq
+    if patch_generate and hasattr(mt, "TasteSpokenLM"):
+        from .generate import generate_kv_cached
+        mt.TasteSpokenLM.generate = generate_kv_cached
     if patch_frontend:
         from .frontend import WhisperFrontendB200
         for modname in ("taste_speech.processing_taste", "taste_speech.data.dataset",
