@@ -237,9 +237,16 @@ typedef struct {
   float* stats_out; void* out_bf16;
 } taste_gemm_ex_t;
 int taste_gemm_ex(const taste_gemm_ex_t* g, void* stream);
-/* Encoder option for A/B timing and tests: 0 = fold self_attn_layer_norm into the fc2 -> QKV GEMM pair when the folded
- * weights are present and the batch has >= 2048 rows (final_layer_norm stays a kernel), 1 = always run the separate
- * LayerNorm kernels, 2 = fold both LayerNorms (measured slower; A/B only). */
+/* Diagnostic switches (taste_*_set_mode): process-wide, read at launch time, NOT synchronised - set them once before
+ * any concurrent use; they exist for A/B timing, for tests that pit two formulations against each other, and as the
+ * documented escape hatch below.  Everything else in this ABI is safe to call concurrently on different streams.
+ *
+ * Encoder: 0 = fold self_attn_layer_norm into the fc2 -> QKV GEMM pair when the folded weights are present and the batch
+ * has >= 2048 rows (final_layer_norm stays a kernel), 1 = always run the separate two-pass LayerNorm kernels, 2 = fold both
+ * LayerNorms (measured slower; A/B only).  The fold rounds the RAW residual rows to the 16-bit operand type and removes
+ * the row mean after the GEMM, so its rounding error scales with |row mean| / row std (tests: Whisper-like rows with
+ * +-300 outlier channels and a half-sigma common offset stay inside the LayerNorm -> GEMM budget); a checkpoint whose
+ * residual rows carry a common-mode offset far above their spread should run with mode 1. */
 int taste_encoder_set_mode(int mode);
 /* Front-end formulation for A/B timing and tests: 0 = split-bf16 DFT on the tcgen05 GEMM kernel when dft_w_bf16 is
  * present (default), 1 = the fp32 folded-DFT FMA kernel.  Process-wide. */

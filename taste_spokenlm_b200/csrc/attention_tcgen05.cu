@@ -64,7 +64,6 @@ struct FaCfg {
   static_assert((NT * 128 * kSoftmaxRegs + 128 * 40) <= 65536, "registers");
 };
 // VAR bits (template parameter; A/B knobs, see launch_attention_tcgen05):
-//   4   in-kernel timeline trace (2 x 128 only)
 //   16  free-running tiles: no ping-pong turns between the softmax warpgroups (the default with 3 x 64)
 //   64  split phases: a row's MUFU pairs first, under the tile's turn (one warp saturates the XU pipe), the turn is
 //       handed over, then the polynomial pairs (FMA pipe) run under the next tile's MUFU phase; without it POLY of
@@ -76,7 +75,6 @@ constexpr int FA_VAR_SPLIT = 64;
 constexpr int FA_VAR_SPEC = 64 | 128;
 constexpr int FA_VAR_FREE = 16;
 struct FaParams {
-  long long* dbg;      // timeline trace (VAR bit 2 only)
   int q_len, kv_len;
   int heads, q_blocks, n_items;      // work item w = (b * heads + head) * q_blocks + qb
   // Ragged queries (the aggregator's cross-attention, CW:361-366 with JES:377-388's dict K/V): utterance b owns the packed
@@ -117,12 +115,6 @@ struct FaItemWalk {
     }
   }
 };
-
-#define FA_TRACE(slot, idx)                                                      \
-  do {                                                                           \
-    if ((VAR & 4) && NT == 2 && p.dbg && blockIdx.x == 0 && lane == 0 && (idx) < 256) \
-      p.dbg[(slot) * 256 + (idx)] = clock64();                                   \
-  } while (0)
 
 // Persistent: one CTA per SM loops over work items (256 queries of one (utterance, head)); TMEM, barriers and the
 // K/V ring live across items, the next item's Q / K / V loads and first QK^T run under the current item's tail, so
@@ -192,7 +184,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
   const uint32_t tmem_base = *tmem_slot;
 
   // Producer and MMA warps run warp-uniform loops and elect one lane around the TMA / tcgen05 instructions (inside an
-  // `if (lane == 0)` region every UTCHMMA is wrapped in an ELECT loop: ~90 cycles per MMA, measured with FA_TRACE).
+  // `if (lane == 0)` region every UTCHMMA is wrapped in an ELECT loop: ~90 cycles per MMA, measured with an in-kernel clock64 trace in round 1).
   // Register reallocation between warpgroups (setmaxnreg): the softmax threads hold a whole score row and schedule
   // their exp2 phase far better with 232 registers (2 x 128; 152 for 3 x 64); the TMA / MMA warps need almost nothing.
   // 256 x 232 + 128 x 40 <= 384 x 168.  (The instruction sits at the head of each role's branch: ptxas budgets
@@ -304,12 +296,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
       const bool more = g + 1 < total_g;
       if (more) wait_inputs_next(&s_free[i], uint32_t(g & 1));
       else mbar_wait(&s_free[i], uint32_t(g & 1));
-      FA_TRACE(2 + i, g * 8 + 0);
       tc_fence_after();
       if (more) issue_qk_next();          // next block's scores first: the softmax warps wait on these
-      FA_TRACE(2 + i, g * 8 + 1);
       mbar_wait(&p_full[i], uint32_t(g & 1));
-      FA_TRACE(2 + i, g * 8 + 2);
       tc_fence_after();
       const uint64_t dv = dv_base + uint64_t(stage) * kStageStep;
       if (elect_one()) {
@@ -322,7 +311,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
         if (j == n_blocks - 1) umma_commit(&q_empty[qbuf]);              // likewise
       }
       __syncwarp();
-      FA_TRACE(2 + i, g * 8 + 3);
       if (++j == n_blocks) {
         j = 0;
         qbuf ^= 1;
@@ -368,7 +356,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
       // memory (128-byte swizzle: chunk ^ (row & 7), conflict-free 16-byte stores) and lane 0 hands it to the TMA,
       // which also clips the rows past the utterance's last query.
       mbar_wait(&o_full[i], uint32_t((g - 1) & 1));
-      FA_TRACE(4 + i, out_it * 8 + 0);
       tc_fence_after();
       const float inv = out_inv;
       if (p.cu_q) {
@@ -416,14 +403,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
       }
       tc_fence_before();      // O_i has been read: the next item's first P V (accumulate = 0) may overwrite it; that MMA
                               // is issued only after this warpgroup's next p_full arrive, which follows in program order
-      FA_TRACE(4 + i, out_it * 8 + 2);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0 && out_row < p.q_len) {
         tma_store_3d(&tma_o, stage_out, out_head * FA_HD, out_row, out_b);      // lane 0: `row` is the warp's first query
         tma_store_commit();
       }
-      FA_TRACE(4 + i, out_it * 8 + 3);
     };
     FaItemWalk walk(int(blockIdx.x), int(gridDim.x), p.q_blocks, p.heads);
     for (int it = 0; it < my_items; ++it, walk.next(p.q_blocks, p.heads)) {
@@ -435,11 +420,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
       bool pending = false;          // P of the previous block written but not yet signalled
 
       for (int j = 0; j < n_blocks; ++j, ++g) {
-        FA_TRACE(i, g * 8 + 0);
         // (a successful mbarrier.try_wait still takes ~150 cycles to return - in-kernel timeline - so the polls of
         // barriers that are normally complete by the time they are needed are issued early and consumed here)
         if (!s_ready) mbar_wait(&s_full[i], uint32_t(g & 1));
-        FA_TRACE(i, g * 8 + 1);
         tc_fence_after();
         // The whole S row (128 fp32) is read into registers ONCE: one exposed TMEM latency per block, and the S tile
         // can be handed back to the MMA warp immediately, so the next block's QK^T runs under this block's entire
@@ -465,7 +448,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[i]);       // every read of S has landed: the next QK^T may overwrite it
-        FA_TRACE(i, g * 8 + 3);
         if (valid < FA_BK) {
 #pragma unroll
           for (int c = 0; c < NC; ++c)
@@ -570,9 +552,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
             if (kTurn && c == 0 && j > 0) {
               // Only now is the previous block's P V needed: P_i has been consumed (it may be overwritten) and O_i is
               // stable (it may be rescaled).  On the first block of an item the output pass below already waited.
-              FA_TRACE(i, g * 8 + 4);
               if (!o_ready) mbar_wait(&o_full[i], uint32_t((g - 1) & 1));
-              FA_TRACE(i, g * 8 + 5);
               tc_fence_after();
               if (rescale) rescale_o(alpha);
             }
@@ -597,7 +577,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
         float alpha = 1.0f;
         if (exact) {
           const float mx = row_max();
-          FA_TRACE(i, g * 8 + 2);
           alpha = adopt_max(mx, any_grow);
         }
         // Ping-pong: the two tiles' exp2 phases alternate (named barriers 1 / 2, FA3-style) instead of drifting into
@@ -624,7 +603,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
           __syncwarp();
           if (lane == 0) mbar_arrive(&p_full[i]);
         }
-        FA_TRACE(i, g * 8 + 6);
       }
 
       // (Deferring this pass into the next item's first block, under its loads and row maximum, hides the wait for the
@@ -719,7 +697,6 @@ int launch_attention_tcgen05(const AttnDesc& d, cudaStream_t stream) {
   if ((rc = make_map(enc, &mv, d.v, d.heads, d.kv_len, d.batch, d.ldv, want_bk))) return rc;
   if ((rc = make_map(enc, &mo, d.o, d.heads, q_rows, q_batch, d.ldo, 32))) return rc;      // one warp's rows per store
   FaParams p;
-  p.dbg = nullptr;
   p.q_len = d.q_len;
   p.kv_len = d.kv_len;
   p.heads = d.heads;

@@ -84,17 +84,28 @@ def test_gemm(lib, m, n, k, epi, mode):
     assert _rel(out.float(), ref) < tol
 
 
-@pytest.mark.parametrize("m,d,n", [(2048, 1280, 3840), (3000, 256, 512), (5000, 1280, 5120)])
+@pytest.mark.parametrize("m,d,n,dist", [(2048, 1280, 3840, "normal"), (3000, 256, 512, "normal"), (5000, 1280, 5120, "normal"),
+                                        (2048, 1280, 3840, "outliers")])
 @pytest.mark.parametrize("gelu", [0, 1])
-def test_gemm_layernorm_folding(lib, m, d, n, gelu):
+def test_gemm_layernorm_folding(lib, m, d, n, gelu, dist):
     """Producer GEMM (residual epilogue) emits h, bf16(h) and per-128-column row statistics; consumer GEMM on the RAW
-    bf16 rows with gamma-folded weights reproduces Linear(LayerNorm(h)) (include/taste_b200.h: taste_gemm_ex)."""
+    bf16 rows with gamma-folded weights reproduces Linear(LayerNorm(h)) (include/taste_b200.h: taste_gemm_ex).
+
+    `outliers`: a Whisper-like residual stream - a few massive-activation channels (+-300 against a unit
+    bulk) and a common-mode row offset of half a standard deviation.  The fold rounds the RAW rows to bf16 and removes
+    the mean after the GEMM, so its error grows with |row mean| / row std; it must stay within the same budget as
+    LayerNorm -> bf16 -> GEMM here.  (Rows whose mean dwarfs their spread need `taste_encoder_set_mode(1)`.)"""
     torch.manual_seed(m + d + n + gelu)
     kk = 256
     a = (torch.randn(m, kk, device="cuda") * 0.5).bfloat16()
     wo = (torch.randn(d, kk, device="cuda") / math.sqrt(kk)).bfloat16()
     bo = torch.randn(d, device="cuda") * 0.1
     h0 = torch.randn(m, d, device="cuda") * 2.0 + 0.3
+    if dist == "outliers":
+        h0 = torch.randn(m, d, device="cuda")
+        for c, v in ((7, 300.0), (500, -260.0), (777, 120.0), (1200, -90.0)):
+            h0[:, c] = v * (1.0 + 0.05 * torch.randn(m, device="cuda"))
+        h0 = h0 + 0.5 * h0.std(dim=1, keepdim=True)
     h = h0.clone()
     hb_buf = torch.full((m + 64, d), 7.0, device="cuda").bfloat16()
     hb = hb_buf[32:32 + m]
