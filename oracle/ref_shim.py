@@ -176,9 +176,12 @@ def import_modeling_taste():
     install()
     name = "taste_speech.modeling_taste"
     if name not in sys.modules:
+        try:                                       # the real config classes import cleanly (transformers only)
+            importlib.import_module("taste_speech.configuration_taste")
+        except Exception:
+            _stub("taste_speech.configuration_taste", TasteConfig=object, TasteAudioTowerConfig=object,
+                  TasteSpeechDecoderConfig=object, TasteSpokenLMConfig=object)
         for sub, attrs in (
-            ("taste_speech.configuration_taste", dict(TasteConfig=object, TasteAudioTowerConfig=object,
-                                                      TasteSpeechDecoderConfig=object, TasteSpokenLMConfig=object)),
             ("taste_speech.modules_taste.cosyvoice.encoder", dict(ConformerEncoder=object, TransformerEncoder=object)),
             ("taste_speech.modules_taste.cosyvoice.label_smoothing_loss", dict(LabelSmoothingLoss=object)),
             ("taste_speech.modules_taste.cosyvoice.utils", dict(IGNORE_ID=-1, th_accuracy=None)),
