@@ -393,7 +393,13 @@ class TowerEngine(FrontendEngine):
             raise ValueError("asr_token_lengths out of range")
         cu_np = np.zeros(B + 1, dtype=np.int32)
         cu_np[1:] = np.cumsum(lengths_host + 5)
-        meta = torch.from_numpy(np.concatenate([cu_np, lengths_host.astype(np.int32)])).to(dev, non_blocking=True)
+        # pinned staging from torch's caching host allocator (it keeps the block alive until the copy has run), so the
+        # H2D of the two small index vectors is truly asynchronous
+        meta_h = torch.empty(2 * B + 1, dtype=torch.int32, pin_memory=True)
+        meta_np = meta_h.numpy()
+        meta_np[: B + 1] = cu_np
+        meta_np[B + 1:] = lengths_host
+        meta = meta_h.to(dev, non_blocking=True)
         cu, lens32 = meta[: B + 1], meta[B + 1:]
         sum_tokens, max_tokens = int(cu_np[-1]), int(lengths_host.max()) + 5
         tokens = self.assemble_tokens(ids_dev, lens32, cu, sum_tokens)
