@@ -270,9 +270,28 @@ def measure_config5(tower, fe, batch, dev, args):
                 past = out.past_key_values
                 lm.lm_head(out.last_hidden_state[:, -1:])
 
+        from taste_spokenlm_b200.generate import _GraphedDecoder
+        graphed = {}
+
+        def generate_kv_cached_graph():                # + the one-position step replayed from a CUDA graph (static KV cache)
+            dec = graphed.get("dec")
+            if dec is None:
+                dec = graphed["dec"] = _GraphedDecoder(lm.model, dev, torch.bfloat16, L + new_tokens + 8)
+            out = dec.prefill(emb[:, :L])
+            lm.lm_head(out.last_hidden_state[:, -1:])
+            for k in range(1, new_tokens):
+                out = dec.step(emb[:, L + k - 1: L + k])
+                lm.lm_head(out.last_hidden_state[:, -1:])
+
         pre_ms = timed(prefill, 5)
         gen_ms = timed(generate_like_reference, 2)
         gen_kv_ms = timed(generate_kv_cached, 2)
+        try:
+            gen_graph_ms = timed(generate_kv_cached_graph, 3)
+            res.update({"lm_generate_kv_cached_cuda_graph_ms": gen_graph_ms,
+                        "tokenizer_share_of_completion_kv_cached_cuda_graph": tok_ms / (tok_ms + gen_graph_ms)})
+        except Exception as e:  # noqa: BLE001
+            res["lm_graph_error"] = f"{type(e).__name__}: {str(e)[:200]}"
         res.update({"lm_prefill_ms": pre_ms, "lm_generate_ms": gen_ms, "lm_new_tokens": new_tokens,
                     "lm_generate_kv_cached_ms": gen_kv_ms,
                     "tokenizer_share_of_completion_kv_cached": tok_ms / (tok_ms + gen_kv_ms),

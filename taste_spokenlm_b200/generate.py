@@ -7,6 +7,11 @@ position (`TasteSampler.text_sample` / `taste_sample` index `[:, -1:]`, sampler.
 position-wise), so the loop below feeds the prompt once, keeps the backbone's `past_key_values`, and afterwards forwards
 only the one new fused embedding: L + n token-forwards, same tokens.
 
+On a GPU the one-position step is additionally captured in a **CUDA graph** over a static KV cache (`_GraphedDecoder`):
+a 1 B-parameter Llama at batch 1 is launch-bound in eager PyTorch (~7 ms per forward whether it carries 1 or 100
+positions), so the cache alone saves FLOPs but no time; replaying the captured step costs what its ~200 small
+kernels and the 2.4 GB of weights cost the GPU.  `cuda_graph=False` (or a CPU backbone) keeps the eager cached loop.
+
 It is host-side orchestration over the reference's own modules — the Llama backbone, `lm_head`, the bridge
 (`extract_for_bridge_out_llm`, `fuse_for_bridge_in_llm`), `encode_audio`, `_prepare_single` and `TasteSampler` are called
 exactly as the reference calls them — and it returns the same 4-tuple.  `tower.install(patch_generate=True)` binds it as
@@ -29,6 +34,89 @@ def _last_position(outputs, want_layers: bool):
     if want_layers and getattr(outputs, "hidden_states", None) is not None:
         hs = tuple(h[:, -1:, :] for h in outputs.hidden_states)
     return SimpleNamespace(last_hidden_state=outputs.last_hidden_state[:, -1:, :], hidden_states=hs)
+
+
+class _EagerDecoder:
+    """KV-cached backbone steps with the backbone's own dynamic cache (any device)."""
+
+    def __init__(self, backbone):
+        self.backbone, self.past = backbone, None
+
+    def prefill(self, embeds):
+        return self.step(embeds)
+
+    def step(self, embeds):
+        out = self.backbone(inputs_embeds=embeds, past_key_values=self.past, use_cache=True, attention_mask=None,
+                            output_hidden_states=True, return_dict=True)
+        self.past = out.past_key_values
+        return out
+
+
+class _GraphedDecoder:
+    """The same steps over a static KV cache, the one-position step captured once in a CUDA graph and replayed.
+
+    Static buffers: the new position's embedding `x [1, 1, H]` (input), the backbone's `last_hidden_state` and per-layer
+    `hidden_states` of that position (outputs, overwritten by the next replay; every consumer reads them before the next
+    step), and the cache itself: transformers' `StaticCache` keeps the number of cached positions in a per-layer DEVICE
+    tensor (`cumulative_length`, advanced in place by every update) from which the captured forward derives the write
+    slot, the rotary position and the attention mask over the not-yet-written tail - so a replay is position-correct with
+    no host-side argument.  When the cache fills up the history is re-fed into one twice as long (the reference has no
+    length limit either)."""
+
+    def __init__(self, backbone, device, dtype, max_len):
+        from transformers import StaticCache
+        self.backbone, self.device, self.dtype = backbone, device, dtype
+        self.max_len = int(max_len)
+        self.cache = StaticCache(config=backbone.config, max_cache_len=self.max_len)
+        hid = backbone.config.hidden_size
+        self.x = torch.zeros(1, 1, hid, dtype=dtype, device=device)
+        self.graph, self.out = None, None
+        self.length = 0
+        self.history = []
+
+    def _forward(self, embeds):
+        return self.backbone(inputs_embeds=embeds, past_key_values=self.cache, use_cache=True, attention_mask=None,
+                             output_hidden_states=True, return_dict=True)
+
+    def _set_length(self, n):
+        for layer in self.cache.layers:                  # in place: the captured graph reads these addresses
+            layer.cumulative_length.fill_(int(n))
+
+    def prefill(self, embeds):
+        n = embeds.shape[1]
+        if n > self.max_len:
+            raise ValueError(f"prompt of {n} positions exceeds the static cache ({self.max_len})")
+        self._set_length(0)                              # a reused decoder starts over; stale slots are masked out
+        out = self._forward(embeds)
+        self.length = n
+        self.history = [embeds]
+        return out
+
+    def _capture(self):
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):                    # warm-up outside the capture (lazy initialisations, autotuning);
+            for _ in range(2):                           # each run writes slot `length` (same values) and advances the
+                self._forward(self.x)                    # counters, which are put back
+                self._set_length(self.length)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = self._forward(self.x)
+        self._set_length(self.length)                    # capture does not execute, but keep the invariant explicit
+
+    def step(self, embeds):
+        if self.length >= self.max_len:                  # grow: replay the history into a cache twice as long
+            bigger = _GraphedDecoder(self.backbone, self.device, self.dtype, 2 * self.max_len)
+            bigger.prefill(torch.concat(self.history, dim=1))
+            self.__dict__.update(bigger.__dict__)
+        self.x.copy_(embeds)
+        if self.graph is None:
+            self._capture()
+        self.graph.replay()                              # writes slot `length`, advances the device-side counters
+        self.length += 1
+        self.history.append(embeds.clone())
+        return self.out
 
 
 def _prompt(lm, embed_tokens, vq_module, mode, llm_indices, llm_token_ids, llm_token_lengths, llm_word_ids, kwargs, dtype,
@@ -88,12 +176,17 @@ def generate_kv_cached(self, vq_module, conditional_mode, llm_indices=None, llm_
 
     taste_rows, token_ids, word_ids = [], [], []
     last_audio = None
-    past = None
     pad_audio = self.pad_audio_unit_embed.reshape(1, 1, -1)
+    use_graph = bool(kwargs.get("cuda_graph", True)) and torch.device(device).type == "cuda"
+    if use_graph:
+        limit = int(getattr(backbone.config, "max_position_embeddings", 1 << 30))
+        decoder = _GraphedDecoder(backbone, device, dtype, min(limit, step_embeds.shape[1] + 24 * int(extra_words) + 256))
+    else:
+        decoder = _EagerDecoder(backbone)
+    first = True
     while True:
-        out = backbone(inputs_embeds=step_embeds, past_key_values=past, use_cache=True, attention_mask=None,
-                       output_hidden_states=want_layers, return_dict=True)
-        past = out.past_key_values                      # the only state carried between steps
+        out = decoder.prefill(step_embeds) if first else decoder.step(step_embeds)   # the KV cache is the only carried state
+        first = False
         newest = _last_position(out, want_layers)
         text_logits = lm_head(newest.last_hidden_state)
         taste_logits, _ = self.extract_for_bridge_out_llm(newest, vq_module)
