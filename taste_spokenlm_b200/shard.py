@@ -421,7 +421,6 @@ class ShardWriter:
         if not files:
             raise RuntimeError("nothing written")
         from datasets import Features
-        from datasets.fingerprint import generate_fingerprint  # noqa: F401  (only to fail early if datasets is too old)
         schema = self._read_table(files[0]).schema
         info = {"citation": "", "description": "", "features": Features.from_arrow_schema(schema).to_dict(),
                 "homepage": "", "license": ""}

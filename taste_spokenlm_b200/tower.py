@@ -115,6 +115,11 @@ class WhisperAudioJointEncoderSegmenterB200(nn.Module):
 
     _tower_ref = None            # weak reference to the owning TasteAudioTowerB200 (which owns the kernel engine)
 
+    def __getstate__(self):      # weak references do not pickle / deep-copy: the owning tower re-binds them
+        d = self.__dict__.copy()
+        d["_tower_ref"] = None
+        return d
+
     def forward(self, audio_features, audio_features_lengths, asr_token_ids=None, asr_token_lengths=None,
                 asr_word_ids=None, whisper_text_token=None, whisper_text_token_len=None, words_index=None,
                 word_ids=None, **kwargs):
@@ -198,6 +203,11 @@ class ResidualVQB200(nn.Module):
         self.mlps = nn.ModuleList([_UnusedMLP(codebook_dim) for _ in range(num_quantizers - 1)])
         self._tower_ref = None           # weak reference to the owning TasteAudioTowerB200 (set in its constructor)
 
+    def __getstate__(self):      # weak references do not pickle / deep-copy: the owning tower re-binds them
+        d = self.__dict__.copy()
+        d["_tower_ref"] = None
+        return d
+
     @property
     def codebook_size(self):
         return self.layers[0]._codebook.embed.shape[1]
@@ -278,6 +288,11 @@ def _whisper_geometry(model_name_or_path: Optional[str], override: Optional[dict
     return g
 
 
+def _invalidate_after_load(module, incompatible_keys):
+    """load_state_dict post-hook (a module-level function so that the tower stays picklable / deep-copyable)."""
+    module.invalidate_engine()
+
+
 class TasteAudioTowerB200(nn.Module):
     def __init__(
         self,
@@ -329,15 +344,28 @@ class TasteAudioTowerB200(nn.Module):
             self.quantization_on = False
         self.audio_dropout_ratio = audio_dropout_ratio
         self.add_eos = True
-        import weakref
-        self.audio_joint_encoder_segmenter._tower_ref = weakref.ref(self)
-        if self.quantization_on:
-            self.vq.rvq._tower_ref = weakref.ref(self)
+        self._bind_children()
         self._engine: Optional[TowerEngine] = None
         self._engine_key = None
         self._state_epoch = 0
         self._sentinels = None
-        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_engine())
+        self.register_load_state_dict_post_hook(_invalidate_after_load)
+
+    def _bind_children(self) -> None:
+        """The segmenter and the RVQ reach the kernels through their owning tower (weak references: no cycle in state)."""
+        import weakref
+        self.audio_joint_encoder_segmenter._tower_ref = weakref.ref(self)
+        if self.quantization_on:
+            self.vq.rvq._tower_ref = weakref.ref(self)
+
+    def __getstate__(self):      # pickling / copy.deepcopy: the packed kernel-side weights are rebuilt on first use
+        d = self.__dict__.copy()
+        d["_engine"], d["_engine_key"], d["_sentinels"] = None, None, None
+        return d
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._bind_children()
 
     # ---- construction helpers ----
     @classmethod

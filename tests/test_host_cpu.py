@@ -161,3 +161,21 @@ def test_word_runs_padded_row_quirk():
     assert O.word_runs(torch.tensor([0, 0, 0, 0]), 2) == []
     assert O.word_runs(torch.tensor([0, 0]), 2) == [(0, 2)]
     assert O.word_runs(torch.tensor([0, 1, 1, 2, 2, 2, 0, 0]), 7) == [(1, 3), (3, 6)]
+
+
+def test_tower_deepcopy_and_pickle_rebind_children():
+    """The RVQ / segmenter reach the kernels through a weak reference to their owning tower: a copied or unpickled tower
+    must own its children's references (not share the original's engine) and drops the packed weights."""
+    import copy
+    import io
+    from taste_spokenlm_b200.tower import TasteAudioTowerB200
+    t = TasteAudioTowerB200.from_config(synth.TINY)
+    t2 = copy.deepcopy(t)
+    assert t2.vq.rvq._tower_ref() is t2 and t2.audio_joint_encoder_segmenter._tower_ref() is t2
+    assert t.vq.rvq._tower_ref() is t
+    buf = io.BytesIO()
+    torch.save(t, buf)
+    buf.seek(0)
+    t3 = torch.load(buf, weights_only=False)
+    assert t3.vq.rvq._tower_ref() is t3 and t3._engine is None
+    assert set(t3.state_dict()) == set(t.state_dict())
