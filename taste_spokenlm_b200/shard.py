@@ -54,7 +54,7 @@ def pack_results(utt_ids: Sequence[int], indices: Sequence[torch.Tensor]) -> Tup
     return hdr, flat
 
 
-def gather_indices(hdr: torch.Tensor, flat: torch.Tensor, num_q: int, device=None) -> List[Tuple[int, torch.Tensor]]:
+def gather_indices(hdr: torch.Tensor, flat: torch.Tensor, num_q: int, device=None) -> GatheredIndices:
     """All ranks receive every (utterance id, [T, Q] int16 indices), sorted by utterance id.
 
     Two collectives: all_gather of the (n_utts, n_rows) counts, then all_gather of the padded header / index buffers.
@@ -86,18 +86,54 @@ def gather_indices(hdr: torch.Tensor, flat: torch.Tensor, num_q: int, device=Non
     return _unpack(parts)
 
 
-def _unpack(parts) -> List[Tuple[int, torch.Tensor]]:
-    """[(header [n, 2], flat [rows, Q])] per rank -> [(utterance id, [T, Q])] sorted by id (views of one tensor; no
-    per-row copies: with 16 k utterances per job a Python-level slice loop was most of the gather's wall time)."""
+class GatheredIndices:
+    """The job's results, sorted by utterance id, without one Python object per utterance: `ids[i]`, and the `[T_i, Q]`
+    int16 indices of that utterance as a view of one flat tensor.  Behaves like the list of `(utterance id, indices)`
+    pairs it replaces (len / iteration / integer indexing / == []).  With 100 k utterances per job, building that list on
+    every rank was 1.5 s of a 30 s job."""
+
+    def __init__(self, ids: np.ndarray, lens: np.ndarray, flat: torch.Tensor):
+        order = np.argsort(ids, kind="stable")
+        starts = np.zeros(len(ids) + 1, dtype=np.int64)
+        np.cumsum(lens, out=starts[1:])
+        self.ids = ids[order]
+        self._start = starts[:-1][order]
+        self._len = lens[order]
+        self.flat = flat
+
+    def __len__(self):
+        return len(self.ids)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        s = int(self._start[i])
+        return int(self.ids[i]), self.flat[s: s + int(self._len[i])]
+
+    def __iter__(self):
+        for i in range(len(self)):
+            yield self[i]
+
+    def __eq__(self, other):
+        return list(self) == other if isinstance(other, list) else NotImplemented
+
+    def lookup(self, utt_id: int) -> torch.Tensor:
+        i = int(np.searchsorted(self.ids, utt_id))
+        if i >= len(self.ids) or int(self.ids[i]) != int(utt_id):
+            raise KeyError(utt_id)
+        return self[i][1]
+
+
+def _unpack(parts) -> GatheredIndices:
+    """[(header [n, 2], flat [rows, Q])] per rank -> the results sorted by utterance id (views of one tensor)."""
     parts = [(h, f) for h, f in parts if h.shape[0] > 0]
     if not parts:
-        return []
-    hdr = torch.cat([h for h, _ in parts])
+        return GatheredIndices(np.zeros(0, np.int64), np.zeros(0, np.int64), torch.zeros(0, 0, dtype=torch.int16))
+    hdr = torch.cat([h for h, _ in parts]).numpy().astype(np.int64)
     flat = torch.cat([f for _, f in parts])
-    ids = hdr[:, 0].tolist()
-    pieces = torch.split(flat, hdr[:, 1].tolist())
-    order = sorted(range(len(ids)), key=ids.__getitem__)
-    return [(ids[i], pieces[i]) for i in order]
+    return GatheredIndices(hdr[:, 0], hdr[:, 1], flat)
 
 
 class _Slot:
@@ -224,7 +260,7 @@ def _run_pipeline(engine, corpus, owned, batch_size, writer, tm, num_q, map_llm,
         meta["h2d_bytes"] = 4 * B * n + 12 * B * T + 4 * B + (4 * B * meta["L"] + 8 * B if map_llm else 0)
         return meta
 
-    utt_ids, results = [], []
+    res_ids, res_lens, res_rows = [], [], []       # per batch: utterance ids, token counts, ragged [sum T, Q] int16 rows
     tm.setdefault("h2d_bytes", 0)
     tm.setdefault("d2h_bytes", 0)
 
@@ -241,9 +277,10 @@ def _run_pipeline(engine, corpus, owned, batch_size, writer, tm, num_q, map_llm,
             asr = out if not map_llm else None
             if map_llm:            # the gather carries asr-token indices: first token of every word <-> llm word starts
                 asr = s.out_h[B * W * num_q: B * W * num_q + B * meta["T"] * num_q].view(B, meta["T"], num_q).numpy()
-            for row, u in enumerate(blist[i]):
-                utt_ids.append(int(u))
-                results.append(torch.from_numpy(asr[row, : int(meta["lengths_host"][row])].copy()))
+            lens = np.asarray(meta["lengths_host"], dtype=np.int64)
+            res_ids.append(np.asarray(blist[i], dtype=np.int64))
+            res_lens.append(lens)
+            res_rows.append(asr[np.arange(asr.shape[1])[None, :] < lens[:, None]])    # copies out of the staging buffer
         if writer is not None:
             t0 = _now()
             writer.add_batch(blist[i], out, meta["llm_ids"], s.lwid_h[:B, :W].numpy(), meta["llm_lengths_host"])
@@ -288,7 +325,10 @@ def _run_pipeline(engine, corpus, owned, batch_size, writer, tm, num_q, map_llm,
             inflight.append((i, meta))
         while inflight:
             finish(*inflight.popleft())
-    return pack_results(utt_ids, results)
+    if not res_ids:
+        return torch.zeros(0, 2, dtype=torch.int32), torch.zeros(0, num_q, dtype=torch.int16)
+    hdr = torch.from_numpy(np.stack([np.concatenate(res_ids), np.concatenate(res_lens)], axis=1).astype(np.int32))
+    return hdr, torch.from_numpy(np.concatenate(res_rows).reshape(-1, num_q))
 
 
 class ShardWriter:
