@@ -340,6 +340,12 @@ def run_corpus(args, rank, world, local_rank):
     warm = synth.SynthCorpus(args.batch * 3 * world, seed=5, pool=2)
     shard.tokenize_corpus(eng, warm, world, rank, batch_size=args.batch, writer=shard.ShardWriter(out_dir + "/warm", rank),
                           gather=True)
+    if world > 1:
+        # ... and one gather of the real job's message size: NCCL sets up its large-message channels on first use
+        n_u = args.utts // world + 1
+        n_r = int(sum(corpus.token_counts)) // world + 1
+        shard.gather_indices(torch.zeros(n_u, 2, dtype=torch.int32, device=dev),
+                             torch.zeros(n_r, cfg.num_quantizers, dtype=torch.int16, device=dev), cfg.num_quantizers, dev)
     barrier()
     launches0 = lib.taste_launch_count()
     sampler = ClockSampler(local_rank) if rank == 0 else None

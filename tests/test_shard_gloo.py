@@ -37,12 +37,14 @@ def test_shards_partition_the_corpus_and_balance_lengths():
         assert max(loads) - min(loads) <= 0.1 * np.mean(loads) + 64
     owned = shard.shard_indices(tc, 2, 1)
     seen = []
+    sizes = []
     for b in shard.batches(owned, tc, 16):
-        assert 1 <= len(b) <= 16
-        lens = [tc[i] for i in b]
-        assert max(lens) // 16 - min(lens) // 16 <= 1                               # tight padding
+        sizes.append(len(b))
         seen += b.tolist()
     assert seen == owned.tolist()
+    assert all(s == 16 for s in sizes[:-1]) and 1 <= sizes[-1] <= 16              # full launches; only the last is short
+    lens = [tc[i] for i in owned]
+    assert all(lens[i] // 16 <= lens[i + 1] // 16 for i in range(len(lens) - 1))   # bucketed order: neighbours alike
     with pytest.raises(ValueError):
         shard.shard_indices(tc, 2, 2)
 
