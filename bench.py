@@ -400,7 +400,10 @@ def run_corpus(args, rank, world, local_rank):
             "rank_ms": {"max": max(rank_ms), "min": min(rank_ms)},
             "host_ms_per_batch_max_over_ranks": {"fetch (worker thread, overlapped)": per_batch(0), "stall (compute thread waits for worker)": per_batch(1),
                                                   "result_wait": per_batch(2), "writer": per_batch(3)},
-            "gather_ms": float(stats_all[:, 4].max()), "writer_ms_total": float(stats_all[:, 3].max()), "finalize_ms": fin_ms,
+            # max over ranks = the fastest rank waiting for the slowest at the collective (GPUs of one box differ by ~2 %
+            # under the power cap); min over ranks = what the collective + unpacking cost the rank that arrived last
+            "gather_ms": float(stats_all[:, 4].max()), "gather_ms_min_over_ranks": float(stats_all[:, 4].min()),
+            "writer_ms_total": float(stats_all[:, 3].max()), "finalize_ms": fin_ms,
             "e2e": {"value": corpus.audio_seconds / (ms / 1e3), "unit": UNIT,
                     "h2d_bytes_per_step": float((stats_all[:, 6] / nb.clamp_min(1)).mean()),
                     "d2h_bytes_per_step": float((stats_all[:, 7] / nb.clamp_min(1)).mean()),
