@@ -165,10 +165,10 @@ def tokenize_corpus(engine, corpus, world_size: int, rank: int, batch_size: int 
     * host-resident (the corpus job, XV:137-162) — `corpus.fetch_host(indices, slot) -> meta` fills the pinned staging
       tensors of `slot` (`wav_h [B, N] f32`, `ns_h`, `ids_h`, `wid_h`, and for the llm mapping `lwid_h`, `len_h[1]`) and
       returns `{"B", "lengths_host", "max_n", "T", ["L", "llm_lengths_host", "llm_ids"]}`.  Batches run through a
-      double-buffered pipeline: a worker thread fills slot i+1 and enqueues its H2D on a copy stream while the compute
-      stream runs `tokenize_device` (+ `map_to_llm_tokens`) on slot i; every batch makes ONE device-to-host copy
-      (int16 indices into pinned memory), consumed one batch later, so the host never waits on the GPU except for
-      back-pressure.  Results go to `writer.add_batch` (vectorised) and/or are kept for the final gather.
+      three-slot pipeline: a worker thread fills slot i+1 and enqueues its H2D on a copy stream while the compute
+      stream runs `tokenize_device` (+ `map_to_llm_tokens`) on slot i and the host hands batch i-1 to the writer; every
+      batch makes ONE device-to-host copy (int16 indices into pinned memory), consumed one batch later, so the host
+      never waits on the GPU except for back-pressure.  Results go to `writer.add_batch` (vectorised) and/or are kept for the final gather.
     * device-resident (tests, small jobs) — `corpus.load(indices) -> dict` of device tensors, run synchronously.
 
     `timings` (optional dict) receives the per-stage host times in ms: fetch (worker thread), stall (compute thread

@@ -93,6 +93,18 @@ def test_gather_indices_single_process():
     assert shard.gather_indices(hdr0, flat0, 4) == []
 
 
+def test_gathered_indices_container():
+    """The gather returns a lazy, id-sorted view (no per-utterance objects) that still behaves like the list of pairs."""
+    hdr, flat = shard.pack_results([5, 2, 9], [_fake_indices(5, 3), _fake_indices(2, 1), _fake_indices(9, 4)])
+    got = shard.gather_indices(hdr, flat, 4)
+    assert len(got) == 3 and [u for u, _ in got] == [2, 5, 9]
+    assert torch.equal(got[1][1].to(torch.int64), _fake_indices(5, 3)) and got[-1][0] == 9
+    assert torch.equal(got.lookup(9).to(torch.int64), _fake_indices(9, 4))
+    assert [u for u, _ in got[::2]] == [2, 9]
+    with pytest.raises(KeyError):
+        got.lookup(3)
+
+
 def test_shard_writer_streams_and_resumes(tmp_path):
     w = shard.ShardWriter(str(tmp_path), rank=1, flush_every=3)
     rng = np.random.default_rng(0)
