@@ -675,7 +675,12 @@ def main():
             ach, peak, unit = p["flops"] / sec / 1e12, peaks["bf16_tflops_sustained"], "TFLOP/s"
         else:
             ach, peak, unit = p["bytes"] / sec / 1e9, peaks["hbm_gbs"], "GB/s"
-        stages.append({"kernel": p["name"], "launches_per_step": p["launches"] / args.steps,
+        extra = {}
+        if p["name"] in ("attention_encoder", "attention_tcgen05"):
+            # head_dim 64: fp32 scores leave TMEM at 64 B/clk/SM = 16 per clock per SM, half the rate the tensor pipe
+            # consumes them at (profiles/r2_attn_ablation.txt): the kernel's own ceiling
+            extra = {"ceiling": "tmem_read", "ceiling_frac_of_tensor_peak": 0.5, "frac_of_ceiling": ach / (0.5 * peak)}
+        stages.append({**extra, "kernel": p["name"], "launches_per_step": p["launches"] / args.steps,
                        "ms_per_step": p["total_ms"] / args.steps, "share": p["total_ms"] / tot_kernel_ms,
                        "bound": "tensor" if tensor else "hbm", "achieved": ach, "peak": peak, "unit": unit,
                        "frac": ach / peak})
