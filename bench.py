@@ -679,7 +679,10 @@ def main():
         if p["name"] in ("attention_encoder", "attention_tcgen05"):
             # head_dim 64: fp32 scores leave TMEM at 64 B/clk/SM = 16 per clock per SM, half the rate the tensor pipe
             # consumes them at (profiles/r2_attn_ablation.txt): the kernel's own ceiling
-            extra = {"ceiling": "tmem_read", "ceiling_frac_of_tensor_peak": 0.5, "frac_of_ceiling": ach / (0.5 * peak)}
+            mhz = (clocks or {}).get("sm_mhz") or 1400.0
+            n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+            ceil_tf = 16.0 * n_sm * mhz * 1e6 * 256.0 / 1e12          # 16 scores/clk/SM x 4 * head_dim FLOP per score
+            extra = {"ceiling": "tmem_read", "ceiling_tflops_at_sampled_clock": ceil_tf, "frac_of_ceiling": ach / ceil_tf}
         stages.append({**extra, "kernel": p["name"], "launches_per_step": p["launches"] / args.steps,
                        "ms_per_step": p["total_ms"] / args.steps, "share": p["total_ms"] / tot_kernel_ms,
                        "bound": "tensor" if tensor else "hbm", "achieved": ach, "peak": peak, "unit": unit,
