@@ -547,6 +547,7 @@ def main():
 
     # ---- the same step in the other library flavour (same kernels, other 16-bit operand type) ----------------------
     alt = None
+    alt_idx_head = None
     if not args.no_alt_precision:
         other = "fp16" if args.precision == "bf16" else "bf16"
         tower2 = TasteAudioTowerB200.from_config(cfg, precision=other).eval()
@@ -574,6 +575,7 @@ def main():
                "index_agreement_with_headline_arm": float((idx2 == idx).float().mean()),
                "note": "same workload and step, library flavour with the other 16-bit operand type "
                        "(libtaste_b200_f16.so = fp16 operands: the reference's own autocast dtype, JES:133)"}
+        alt_idx_head = idx2[:3].cpu()
         del tower2, eng2
         torch.cuda.empty_cache()
 
@@ -726,6 +728,8 @@ def main():
         got = idx[:reps].cpu()
         ref = torch.stack(ref_rows)
         lvl = [float((got[..., q] == ref[..., q]).float().mean()) for q in range(ref.shape[-1])]
+        if alt is not None and alt_idx_head is not None:
+            alt["parity_check_index_agreement"] = float((alt_idx_head[:reps] == ref).float().mean())
         parity_check = {"utterances": reps, "n_indices": int(ref.numel()), "index_agreement": float((got == ref).float().mean()),
                         "per_level": lvl, "against": "fp32 CPU oracle on utterances 0..2 of the timed batch (device-resident arm; "
                                                      "the e2e arm is asserted bit-equal to it)"}
