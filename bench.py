@@ -452,6 +452,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-config5", action="store_true")
+    ap.add_argument("--no-ragged", action="store_true", help="skip the short config-3 (ragged corpus) measurement")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"],
                     help="library flavour of the headline arm (bf16 = BASELINE config 2's dtype)")
     ap.add_argument("--no-alt-precision", action="store_true", help="skip the second, other-flavour timing of the same step")
@@ -661,6 +662,28 @@ def main():
     if rank == 0 and not args.no_e2e and not args.no_config5:
         config5 = measure_config5(tower, fe, batch, dev, args)
 
+    # ---- BASELINE config 3 in short: 512 ragged utterances through the corpus driver on this rank (full job: --workload corpus)
+    ragged = None
+    if rank == 0 and not args.no_e2e and not args.no_ragged and args.batch >= 8:
+        try:
+            from taste_spokenlm_b200 import shard
+            rc = synth.SynthCorpus(8 * args.batch, seed=4, pool=8)
+            shard.tokenize_corpus(eng, synth.SynthCorpus(2 * args.batch, seed=5, pool=2), 1, 0, batch_size=args.batch, gather=False)
+            torch.cuda.synchronize()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            got = shard.tokenize_corpus(eng, rc, 1, 0, batch_size=args.batch, gather=False)
+            r1.record()
+            torch.cuda.synchronize()
+            rms = r0.elapsed_time(r1)
+            ragged = {"utterances": rc.n, "mean_duration_s": rc.audio_seconds / rc.n, "mean_tokens": float(np.mean(rc.token_counts)),
+                      "real_audio_s_per_s": rc.audio_seconds / (rms / 1e3), "window_audio_s_per_s": rc.n * UTT_SECONDS / (rms / 1e3),
+                      "ms_per_batch": rms / (rc.n / args.batch), "complete": len(got) == rc.n,
+                      "api": "shard.tokenize_corpus: host-resident ragged audio (durations U[1,30] s), pinned H2D pipeline, one D2H per "
+                             "batch; every utterance still costs one 30 s encoder window (SURVEY 0.3)"}
+        except Exception as e:  # noqa: BLE001
+            ragged = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -742,7 +765,7 @@ def main():
         "tflops_per_gpu": flops_per_utt * (value / UTT_SECONDS / world) / 1e12,
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "stages": stages,
         "cpu_baseline": cpu_baseline, "parity_check": parity_check, "alt_precision": alt,
-        "latency_b1_ms": lat_ms, "config5": config5,
+        "latency_b1_ms": lat_ms, "config5": config5, "ragged_config3": ragged,
     }
     if args.layers != 32:
         line["INVALID"] = "debug run with a reduced layer count; not the named config"
