@@ -361,9 +361,11 @@ class SynthCorpus:
         tc = np.asarray([self.token_counts[i] for i in idx], dtype=np.int64)
         T, L = int(tc.max()), int(self.llm_counts[idx].max())
         wav, ids, wid, lwid = slot.wav_h.numpy(), slot.ids_h.numpy(), slot.wid_h.numpy(), slot.lwid_h.numpy()
+        with_llm = lwid.shape[1] >= L                 # the driver sizes the llm staging only when it maps to llm tokens
         ids[:B, :T] = 0
         wid[:B, :T] = 0
-        lwid[:B, :L] = 0
+        if with_llm:
+            lwid[:B, :L] = 0
         llm_ids = np.zeros((B, L), dtype=np.int64)
         for r, u in enumerate(idx):
             n = int(self.n_samples[u])
@@ -371,9 +373,10 @@ class SynthCorpus:
             a0, a1 = self.off[u], self.off[u + 1]
             ids[r, : a1 - a0] = self.ids[a0:a1]
             wid[r, : a1 - a0] = self.wid[a0:a1]
-            l0, l1 = self.llm_off[u], self.llm_off[u + 1]
-            lwid[r, : l1 - l0] = self.llm_wid[l0:l1]
-            llm_ids[r, : l1 - l0] = self.llm_ids[l0:l1]
+            if with_llm:
+                l0, l1 = self.llm_off[u], self.llm_off[u + 1]
+                lwid[r, : l1 - l0] = self.llm_wid[l0:l1]
+                llm_ids[r, : l1 - l0] = self.llm_ids[l0:l1]
         slot.ns_h.numpy()[:B] = self.n_samples[idx]
         slot.len_h.numpy()[0, :B] = tc
         slot.len_h.numpy()[1, :B] = self.llm_counts[idx]
