@@ -702,12 +702,10 @@ def main():
             ach, peak, unit = p["bytes"] / sec / 1e9, peaks["hbm_gbs"], "GB/s"
         extra = {}
         if p["name"] in ("attention_encoder", "attention_tcgen05"):
-            # head_dim 64: fp32 scores leave TMEM at 64 B/clk/SM = 16 per clock per SM, half the rate the tensor pipe
-            # consumes them at (profiles/r2_attn_ablation.txt): the kernel's own ceiling
-            mhz = (clocks or {}).get("sm_mhz") or 1400.0
-            n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-            ceil_tf = 16.0 * n_sm * mhz * 1e6 * 256.0 / 1e12          # 16 scores/clk/SM x 4 * head_dim FLOP per score
-            extra = {"ceiling": "tmem_read", "ceiling_tflops_at_sampled_clock": ceil_tf, "frac_of_ceiling": ach / ceil_tf}
+            # head_dim 64: 16 ex2 per clock per SM against 32 scores per clock for the tensor pipe; with 4 of every 16
+            # exponentials on the FMA pipe the MUFU caps the kernel at 2/3 of the tensor peak
+            extra = {"ceiling": "mufu_ex2 (16/clk/SM, 12 of 16 exponentials)", "ceiling_frac_of_tensor_peak": 2.0 / 3.0,
+                     "frac_of_ceiling": ach / (peak * 2.0 / 3.0)}
         stages.append({**extra, "kernel": p["name"], "launches_per_step": p["launches"] / args.steps,
                        "ms_per_step": p["total_ms"] / args.steps, "share": p["total_ms"] / tot_kernel_ms,
                        "bound": "tensor" if tensor else "hbm", "achieved": ach, "peak": peak, "unit": unit,
