@@ -12,6 +12,6 @@ python - <<PY
 import json
 d=json.load(open('gpurun_out/${TAG}_bench.json'))
 print('value',d['value'],'ms/step',d['ms_per_step'],'e2e',d['e2e']['value'], d['clocks'])
-print('alt', d.get('alt_precision')); print('parity', d.get('parity_check')); print('config5', d.get('config5')); print('ragged', d.get('ragged_config3'))
+print('alt', {k: v for k, v in (d.get('alt_precision') or {}).items() if k != 'note'}); print('parity', d.get('parity_check')); print('config5', d.get('config5')); print('ragged', d.get('ragged_config3'))
 for s in d['stages'][:14]: print(s['kernel'], round(s['ms_per_step'],3), round(s['achieved'],1), round(s['frac'],3))
 PY

@@ -116,3 +116,27 @@ def test_assemble_tokens():
     ids = torch.tensor([[5, 6, 7], [9, 0, 0]])
     t = O.assemble_tokens(ids)
     assert t.tolist() == [[50258, 50259, 50360, 50364, 5, 6, 7, 50257], [50258, 50259, 50360, 50364, 9, 0, 0, 50257]]
+
+
+def test_bench_itemises_a_planted_near_miss():
+    """bench.py's `parity_check.misses`: a token moved to the runner-up code of level 1 is reported once, at level 1, with
+    the fp64 margin between the two codes on the oracle's residual (later levels of that token are consequences)."""
+    import bench
+    cfg = synth.TINY
+    W = synth.random_weights(cfg, 1234)
+    b = synth.synth_batch(3, [5.0, 7.0], [20, 20])
+    feats, _ = O.log_mel(b["wav"])
+    out = O.tower_forward(W, b["asr_token_ids"], b["asr_token_lengths"], feats, b["asr_word_ids"], cfg.heads, cfg.enc_layers,
+                          cfg.dec_layers, cfg.num_quantizers, cfg.target_hidden_layer, stages=True)
+    ref, agg = out["quantized_indices"], out["_aggregated"]
+    r = agg[0, 5].double() @ W["vq.rvq.project_in.weight"].double().T + W["vq.rvq.project_in.bias"].double()
+    r = r - W["vq.rvq.layers.0._codebook.embed"][0].double()[ref[0, 5, 0]]
+    d = (r[None] - W["vq.rvq.layers.1._codebook.embed"][0].double()).norm(dim=1)
+    order = d.argsort()
+    assert int(order[0]) == int(ref[0, 5, 1])
+    got = ref.clone()
+    got[0, 5, 1], got[0, 5, 2] = order[1], (ref[0, 5, 2] + 1) % 512
+    assert bench.itemise_misses(W, ref, agg, ref) == []
+    (m,) = bench.itemise_misses(W, ref, agg, got)
+    assert (m["utt"], m["t"], m["level"]) == (0, 5, 1)
+    assert abs(m["margin_rel"] - float((d[order[1]] - d[order[0]]) / d[order[0]])) < 1e-12
