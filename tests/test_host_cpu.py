@@ -13,6 +13,34 @@ from taste_spokenlm_b200 import _lib, mel, synth
 torch.set_grad_enabled(False)
 
 
+def test_public_header_is_plain_c(tmp_path):
+    """include/taste_b200.h is the binding surface for any host language: it must compile as strict C99 on its own and
+    link against the built library from a C translation unit (no C++ types, no torch, no CUDA headers)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi.c"
+    src.write_text('#include "taste_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) {\n'
+                   '  taste_weights_t w; (void)w;\n'
+                   '  printf("%d %d %d\\n", taste_abi_version(), TASTE_ABI_VERSION, taste_operand_dtype());\n'
+                   '  return taste_abi_version() == TASTE_ABI_VERSION ? 0 : 1;\n}\n')
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+                    "-fsyntax-only", str(src)], check=True)
+    for flavour, code in (("bf16", 0), ("fp16", 1)):
+        so = _lib.LIB_PATHS[flavour]
+        if not os.path.exists(so):
+            pytest.skip("library not built")
+        exe = tmp_path / f"abi_{flavour}"
+        subprocess.run([gcc, "-std=c99", "-I", os.path.join(root, "include"), str(src), "-o", str(exe), so,
+                        f"-Wl,-rpath,{os.path.dirname(so)}"], check=True)
+        out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+        assert out == ["4", "4", str(code)]
+
+
 def test_library_exports_every_declared_symbol(built_lib):
     declared = _lib.declared_symbols()
     assert len(declared) >= 18
