@@ -179,11 +179,12 @@ class ResampleMeanB200:
         nin_d = meta[2 * B + 1:].to(torch.int32)
         tgt = self.output_lengths(n_in, orig_freq)
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        _lib.check(self.lib.taste_resample_mean_f32(
-            _lib.ptr(packed), _lib.ptr(off_d), _lib.ptr(ch_d), _lib.ptr(nin_d), B, tb["orig"], tb["new"], tb["width"],
-            _lib.ptr(tb["taps_dev"]), _lib.ptr(tb["kstart_dev"]), tb["knz"], tb["knz_ld"], int(tgt.max()) if B else 0,
-            int(offsets[-1]), int(np.minimum(tgt, self.wav_stride).sum()), _lib.ptr(out), out.stride(0), _lib.ptr(n_out),
-            stream), "taste_resample_mean_f32")
+        with torch.cuda.device(self.device):            # the library configures and launches on the CURRENT device
+            _lib.check(self.lib.taste_resample_mean_f32(
+                _lib.ptr(packed), _lib.ptr(off_d), _lib.ptr(ch_d), _lib.ptr(nin_d), B, tb["orig"], tb["new"], tb["width"],
+                _lib.ptr(tb["taps_dev"]), _lib.ptr(tb["kstart_dev"]), tb["knz"], tb["knz_ld"], int(tgt.max()) if B else 0,
+                int(offsets[-1]), int(np.minimum(tgt, self.wav_stride).sum()), _lib.ptr(out), out.stride(0),
+                _lib.ptr(n_out), stream), "taste_resample_mean_f32")
         return out, torch.clamp(n_out, max=self.wav_stride)
 
     def __call__(self, arrays: Sequence[np.ndarray], orig_freq: int, out: Optional[torch.Tensor] = None):

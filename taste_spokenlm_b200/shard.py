@@ -198,8 +198,9 @@ def tokenize_corpus(engine, corpus, world_size: int, rank: int, batch_size: int 
     else:
         if writer is not None and map_llm is False:
             raise ValueError("the writer stores llm-token-aligned rows (XV:51-58): map_llm cannot be False with a writer")
-        hdr, flat = _run_pipeline(engine, corpus, owned, batch_size, writer, tm, num_q,
-                                  bool(map_llm) if map_llm is not None else writer is not None, keep_results=gather)
+        with torch.cuda.device(engine.device):          # streams, events and pinned buffers of the pipeline live there
+            hdr, flat = _run_pipeline(engine, corpus, owned, batch_size, writer, tm, num_q,
+                                      bool(map_llm) if map_llm is not None else writer is not None, keep_results=gather)
     if writer is not None:
         t0 = _now()
         writer.flush()
