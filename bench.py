@@ -488,6 +488,8 @@ def main():
     ap.add_argument("--encoder-mode", type=int, default=0, help="taste_encoder_set_mode (A/B runs): 0 default, 1 no LayerNorm folding, 2 fold both")
     args = ap.parse_args()
 
+    if args.layers <= 6:
+        raise SystemExit("--layers must exceed 6: the aggregator's values are the state entering encoder layer 6 (JES:192-193)")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
